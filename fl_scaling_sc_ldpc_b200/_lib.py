@@ -1,0 +1,79 @@
+"""ctypes binding of ``libscldpc.so`` (C ABI declared in ``include/scldpc.h``).
+
+The library is built in-tree (``fl_scaling_sc_ldpc_b200/csrc/Makefile``).  There is no CPU fallback: if the shared
+object is missing, or no CUDA device is visible, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscldpc.so")
+CSRC = os.path.join(HERE, "csrc")
+
+# flags (include/scldpc.h)
+F_TERMINATED = 1
+F_TRAJECTORY = 2
+F_SQUARE = 4
+F_EXP_ALL = 8
+F_CHAN_PACKED = 16
+
+EXPORTS = [
+    "scldpc_last_error", "scldpc_version", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
+    "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
+    "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_decode_host",
+    "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end",
+]
+
+
+class ScldpcError(RuntimeError):
+    pass
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("dv", "dc", "L", "vns_pos", "cns_pos", "n_graphs", "n_words", "n_frames")]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [("vn_cn_dev", ctypes.c_void_p), ("vn_slot_dev", ctypes.c_void_p), ("cn_edge_dev", ctypes.c_void_p),
+                ("chan_dev", ctypes.c_void_p)]
+
+
+class BpOut(ctypes.Structure):
+    _fields_ = [("iters_dev", ctypes.c_void_p), ("residual_dev", ctypes.c_void_p), ("blocks_err_dev", ctypes.c_void_p),
+                ("erasures_exp_dev", ctypes.c_void_p), ("blocks_err_exp_dev", ctypes.c_void_p),
+                ("erasures_p1_dev", ctypes.c_void_p), ("erased_dev", ctypes.c_void_p), ("rows_dev", ctypes.c_void_p),
+                ("max_rows", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile libscldpc.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-s", "-C", CSRC, "clean"], check=True)
+    subprocess.run(["make", "-s", "-C", CSRC, "-j4"], check=True)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ScldpcError(f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              f"or `make -C {CSRC}`; there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.scldpc_last_error.restype = ctypes.c_char_p
+        L.scldpc_bp_workspace_bytes.restype = ctypes.c_size_t
+        L.scldpc_graph_generate_scratch_bytes.restype = ctypes.c_size_t
+        L.scldpc_launch_count.restype = ctypes.c_longlong
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise ScldpcError(f"libscldpc error {rc}: {lib().scldpc_last_error().decode()}")

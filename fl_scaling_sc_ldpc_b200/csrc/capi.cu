@@ -1,0 +1,531 @@
+// capi.cu -- the C ABI of libscldpc.so (declared in include/scldpc.h).  Host-side orchestration only: argument
+// checks, workspace carving, the iteration / window loops and the host-buffer convenience entry point.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "scldpc.h"
+
+namespace scldpc {
+int bp_launch_iteration(int dv, int dc, const BpParams &p, bool traj, bool freeze, cudaStream_t st, int blocks_per_sm);
+int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, cudaStream_t st);
+void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_frames, cudaStream_t st);
+void bp_launch_window_begin(const BpParams &p, int n_frames, cudaStream_t st);
+int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge, int32_t *scratch, int *err_dev, int G,
+                       int n, int nk, int dv, int dc, cudaStream_t st);
+int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
+                   uint64_t first_graph, int tail_biting, cudaStream_t st);
+size_t graph_generate_scratch_words(int G, int L, int cns_pos, int dv, int dc, int tail_biting);
+void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
+                      uint64_t seed, uint64_t first_graph, cudaStream_t st);
+void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
+void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
+}  // namespace scldpc
+
+using namespace scldpc;
+
+namespace scldpc { Profiler g_prof = {0, 0, 0, 0, nullptr, nullptr}; }
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(SCLDPC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                               \
+    } while (0)
+
+static int check_dims(const scldpc_dims_t *d)
+{
+    if (!d) return fail(SCLDPC_EINVAL, "dims is NULL");
+    if (d->dv < 2 || d->dc < 2 || d->L < 1 || d->vns_pos < 1 || d->cns_pos < 1 || d->n_graphs < 1)
+        return fail(SCLDPC_EINVAL, "non-positive dimension");
+    if ((long long)d->vns_pos * d->dv != (long long)d->cns_pos * d->dc)
+        return fail(SCLDPC_EINVAL, "vns_pos*dv (%lld) != cns_pos*dc (%lld)", (long long)d->vns_pos * d->dv,
+                    (long long)d->cns_pos * d->dc);
+    const int W = d->n_words;
+    if (W < 2 || W > SCLDPC_MAX_WORDS || (W & (W - 1))) return fail(SCLDPC_EINVAL, "n_words must be 2, 4, 8 or 16");
+    if (d->n_frames < 0 || d->n_frames > 64 * W) return fail(SCLDPC_EINVAL, "n_frames out of range");
+    if ((long long)d->L * d->vns_pos * d->dv >= INT_MAX / 2) return fail(SCLDPC_EINVAL, "graph too large for int32 edge ids");
+    return 0;
+}
+
+static bool degrees_supported(int dv, int dc)
+{
+    return (dv == 4 && dc == 8) || (dv == 3 && dc == 6) || (dv == 5 && dc == 10) || (dv == 3 && dc == 9) ||
+           (dv == 4 && dc == 12);
+}
+
+static int have_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        return fail(SCLDPC_ECUDA, "no CUDA device available (libscldpc has no CPU fallback)");
+    return 0;
+}
+
+extern "C" const char *scldpc_last_error(void) { return g_err; }
+extern "C" int scldpc_version(void) { return 100; }
+extern "C" int scldpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------------------
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carve {
+    char *base;
+    size_t off;
+    template <typename T>
+    T *take(size_t count)
+    {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += align_up(count * sizeof(T));
+        return p;
+    }
+};
+
+static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *p)
+{
+    const size_t G = d->n_graphs, W = d->n_words, ch = W / 2, lanes = 64 * W;
+    const size_t n = (size_t)d->L * d->vns_pos, nk = (size_t)(d->L + d->dv - 1) * d->cns_pos, E = n * d->dv;
+    Carve c{static_cast<char *>(ws), 0};
+    BpParams q;
+    memset(&q, 0, sizeof q);
+    q.v2c = c.take<u128>(G * (E + 1) * ch);
+    q.c2v = c.take<u128>(G * nk * d->dc * ch);
+    q.latch = (flags & SCLDPC_F_TRAJECTORY) ? c.take<u128>(G * nk * ch) : nullptr;
+    q.active = c.take<u64>(G * W);
+    q.any_new = c.take<u64>(G * W);
+    q.any_er = c.take<u64>(G * W);
+    q.pos_er = c.take<u64>(G * d->L * W);
+    q.ticket = c.take<unsigned>(G);
+    q.alive = c.take<int>(G);
+    q.alive_total = c.take<int>(1);
+    q.cnt_dvn = c.take<int>(G * lanes);
+    q.cnt_deg1 = c.take<int>(G * lanes);
+    q.pos_cnt = c.take<int>(G * d->L * lanes);
+    q.pos_pairs = c.take<int>(G * d->L * lanes);
+    q.work = c.take<long long>(G * lanes);
+    if (p) *p = q;
+    return c.off;
+}
+
+extern "C" size_t scldpc_bp_workspace_bytes(const scldpc_dims_t *d, uint32_t flags)
+{
+    if (check_dims(d)) return 0;
+    return carve(d, flags, nullptr, nullptr);
+}
+
+static int setup_params(const scldpc_dims_t *d, const scldpc_batch_t *b, uint32_t flags, const scldpc_bp_out_t *out,
+                        void *ws, size_t ws_bytes, BpParams *p)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!degrees_supported(d->dv, d->dc)) return fail(SCLDPC_EINVAL, "(dv,dc)=(%d,%d) not instantiated", d->dv, d->dc);
+    if (!b || !b->vn_cn_dev || !b->vn_slot_dev || !b->cn_edge_dev || !b->chan_dev) return fail(SCLDPC_EINVAL, "batch pointer is NULL");
+    if (!out || !out->iters_dev || !out->residual_dev || !out->blocks_err_dev || !out->erasures_exp_dev ||
+        !out->blocks_err_exp_dev || !out->erased_dev)
+        return fail(SCLDPC_EINVAL, "output pointer is NULL");
+    if ((flags & SCLDPC_F_TRAJECTORY) && (!out->rows_dev || out->max_rows <= 0))
+        return fail(SCLDPC_EINVAL, "trajectory mode needs rows_dev and max_rows > 0");
+    if (!ws) return fail(SCLDPC_EINVAL, "workspace is NULL");
+    const size_t need = carve(d, flags, nullptr, nullptr);
+    if (ws_bytes < need) return fail(SCLDPC_ENOMEM, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+    if ((rc = have_device())) return rc;
+    carve(d, flags, ws, p);
+    p->dv = d->dv; p->dc = d->dc;
+    p->n = d->L * d->vns_pos;
+    p->nk = (d->L + d->dv - 1) * d->cns_pos;
+    p->E = p->n * d->dv;
+    p->L = d->L; p->vns_pos = d->vns_pos; p->cns_pos = d->cns_pos;
+    p->G = d->n_graphs; p->W = d->n_words; p->chunks = d->n_words / 2; p->lanes = 64 * d->n_words;
+    p->chunk_shift = 0;
+    while ((1 << p->chunk_shift) < p->chunks) p->chunk_shift++;
+    p->vn_cn = b->vn_cn_dev; p->vn_slot = b->vn_slot_dev; p->cn_edge = b->cn_edge_dev;
+    p->chan = reinterpret_cast<const u128 *>(b->chan_dev);
+    p->x = reinterpret_cast<u128 *>(out->erased_dev);
+    p->iters = out->iters_dev;
+    p->rows = out->rows_dev;
+    p->max_rows = out->rows_dev ? out->max_rows : 0;
+    p->row = -1;
+    return 0;
+}
+
+// pinned flag the host polls
+static thread_local int *g_host_flag = nullptr;
+static int host_flag(int **out)
+{
+    if (!g_host_flag) CU(cudaMallocHost(&g_host_flag, 64));
+    *out = g_host_flag;
+    return 0;
+}
+
+static int blocks_per_sm_env()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("SCLDPC_BLOCKS_PER_SM");
+        v = s ? atoi(s) : 8;
+        if (v < 1) v = 1;
+        if (v > 32) v = 32;
+    }
+    return v;
+}
+
+// ---- graph / channel ------------------------------------------------------------------------------------------
+extern "C" int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_batch_t *b, int32_t *scratch_dev, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!b || !b->vn_cn_dev || !b->vn_slot_dev || !b->cn_edge_dev || !scratch_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = d->L * d->vns_pos, nk = (d->L + d->dv - 1) * d->cns_pos;
+    int *err_dev = nullptr, *hf = nullptr;
+    if ((rc = host_flag(&hf))) return rc;
+    CU(cudaMallocAsync(&err_dev, sizeof(int), st));
+    graph_build_tables(b->vn_cn_dev, b->vn_slot_dev, b->cn_edge_dev, scratch_dev, err_dev, d->n_graphs, n, nk, d->dv, d->dc, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hf, err_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaFreeAsync(err_dev, st));
+    CU(cudaStreamSynchronize(st));
+    if (*hf == 1) return fail(SCLDPC_EGRAPH, "CN index out of range in vn_cn");
+    if (*hf == 2) return fail(SCLDPC_EGRAPH, "a CN has more than dc edges");
+    return 0;
+}
+
+extern "C" int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
+                                     uint64_t first_graph_id, int tail_biting, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!vn_cn_dev || !scratch_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    if (graph_generate(vn_cn_dev, reinterpret_cast<u64 *>(scratch_dev), d->n_graphs, d->L, d->vns_pos, d->cns_pos, d->dv,
+                       d->dc, seed, first_graph_id, tail_biting, static_cast<cudaStream_t>(stream)))
+        return fail(SCLDPC_EINVAL, "cns_pos*dc too large for the key layout");
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting)
+{
+    if (check_dims(d)) return 0;
+    return sizeof(u64) * graph_generate_scratch_words(d->n_graphs, d->L, d->cns_pos, d->dv, d->dc, tail_biting);
+}
+
+extern "C" int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                                       int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
+                                       uint64_t seed, uint64_t first_graph_id, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!chan_dev) return fail(SCLDPC_EINVAL, "chan_dev is NULL");
+    if (!(eps >= 0.0 && eps <= 1.0)) return fail(SCLDPC_EINVAL, "eps must be in [0,1]");
+    if ((rc = have_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t *known_dev = nullptr;
+    if (n_doped > 0 || n_soft > 0) {
+        std::vector<int32_t> known(d->L, 0);
+        for (int i = 0; i < n_doped; i++) {
+            if (doped_pos_host[i] < 0 || doped_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "doped position out of range");
+            known[doped_pos_host[i]] = d->vns_pos;
+        }
+        for (int i = 0; i < n_soft; i++) {
+            if (soft_pos_host[i] < 0 || soft_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "soft-doped position out of range");
+            int c = soft_count_host[i] < 0 ? 0 : (soft_count_host[i] > d->vns_pos ? d->vns_pos : soft_count_host[i]);
+            if (c > known[soft_pos_host[i]]) known[soft_pos_host[i]] = c;
+        }
+        CU(cudaMallocAsync(&known_dev, sizeof(int32_t) * d->L, st));
+        CU(cudaMemcpyAsync(known_dev, known.data(), sizeof(int32_t) * d->L, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // `known` leaves scope below
+    }
+    channel_generate(reinterpret_cast<u64 *>(chan_dev), d->n_graphs, d->L * d->vns_pos, d->n_words, d->n_frames, d->vns_pos,
+                     known_dev, eps, seed, first_graph_id, st);
+    CU(cudaGetLastError());
+    if (known_dev) CU(cudaFreeAsync(known_dev, st));
+    return 0;
+}
+
+extern "C" int scldpc_channel_pack_host(const scldpc_dims_t *d, const uint8_t *erased_host, uint64_t *chan_dev, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!erased_host || !chan_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)d->L * d->vns_pos, bytes = (size_t)d->n_graphs * d->n_frames * n;
+    uint8_t *tmp = nullptr;
+    if (bytes) {
+        CU(cudaMallocAsync(&tmp, bytes, st));
+        CU(cudaMemcpyAsync(tmp, erased_host, bytes, cudaMemcpyHostToDevice, st));
+    }
+    channel_pack(tmp, reinterpret_cast<u64 *>(chan_dev), d->n_graphs, (int)n, d->n_words, d->n_frames, st);
+    CU(cudaGetLastError());
+    if (tmp) CU(cudaFreeAsync(tmp, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- decoders -------------------------------------------------------------------------------------------------
+// Runs up to `cap` flooding iterations over the ranges in *p, polling the device-side "graphs alive" counter every
+// `chunk` iterations (sweeps of a finished graph return at once, so overshoot costs launch latency only).
+static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool freeze, cudaStream_t st, int *launched)
+{
+    int *hf = nullptr, rc;
+    if ((rc = host_flag(&hf))) return rc;
+    const int bps = blocks_per_sm_env();
+    const int chunk = 8;
+    int it = 0;
+    while (it < cap) {
+        const int todo = (cap - it) < chunk ? (cap - it) : chunk;
+        for (int q = 0; q < todo; q++, it++) {
+            p->iter = it;
+            p->max_it = cap;
+            p->first_iter = (it == 0);
+            p->row = traj ? it : -1;
+            if (bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+        }
+        CU(cudaGetLastError());
+        if (it >= cap) break;
+        CU(cudaMemcpyAsync(hf, p->alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*hf == 0) break;
+    }
+    if (launched) *launched += it;
+    return 0;
+}
+
+extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
+                              const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                              int *iters_launched_host, void *stream)
+{
+    BpParams p;
+    int rc = setup_params(d, b, flags, out, workspace_dev, workspace_bytes, &p);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool traj = flags & SCLDPC_F_TRAJECTORY, term = flags & SCLDPC_F_TERMINATED;
+    const int cap = max_it <= 0 ? INT_MAX : max_it;
+    bp_launch_init(p, d->dv, d->dc, traj, d->n_frames, st);
+    CU(cudaGetLastError());
+    p.c0 = 0;
+    p.c1 = term ? p.nk : d->L * d->cns_pos;     // cn_lim (BP_TRAJ.c:944-948)
+    p.v0 = 0;
+    p.v1 = p.n;
+    p.stall_at_first = 1;
+    p.win_edges = 2ll * p.E;
+    int launched = 0;
+    if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, st, &launched))) return rc;
+    BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
+                  (flags & SCLDPC_F_EXP_ALL) ? 1 : 0, 1, 0};
+    if (d->n_frames == 0) CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
+    bp_launch_finalize(d->dv, d->dc, p, fo, st);
+    CU(cudaGetLastError());
+    if (iters_launched_host) *iters_launched_host = launched;
+    return 0;
+}
+
+extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                                const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                                int64_t *edge_updates_host, void *stream)
+{
+    if (flags & SCLDPC_F_TRAJECTORY) return fail(SCLDPC_EINVAL, "the window decoder records no trajectory");
+    if (W < 1) return fail(SCLDPC_EINVAL, "W must be >= 1");
+    BpParams p;
+    int rc = setup_params(d, b, flags, out, workspace_dev, workspace_bytes, &p);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool term = flags & SCLDPC_F_TERMINATED, square = flags & SCLDPC_F_SQUARE;
+    const int cap = max_it <= 0 ? INT_MAX : max_it;
+    const int cap0 = init_it <= 0 ? cap : init_it;                 // BP_SW.c:2099-2102
+    const int ms = d->dv - 1, L = d->L, vp = d->vns_pos, cp = d->cns_pos;
+    const int nwin = square ? L : L + ms;                          // BP_SW.c:672 / BP_FULL.c:668
+    const int cn_clip = term ? p.nk : L * cp;
+    bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
+    CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
+    CU(cudaGetLastError());
+    for (int posW = 0; posW < nwin && d->n_frames > 0; posW++) {
+        long long c0 = (long long)posW * cp, c1 = c0 + (long long)W * cp;
+        if (c1 > cn_clip) c1 = cn_clip;
+        if (c1 < c0) c1 = c0;
+        long long v0, v1;
+        if (square) { v0 = (long long)posW * vp; v1 = v0 + (long long)W * vp; }
+        else if (posW <= ms) { v0 = 0; v1 = (long long)(W + posW) * vp; }
+        else { v0 = (long long)(posW - ms) * vp; v1 = v0 + (long long)(W + ms) * vp; }
+        if (v1 > p.n) v1 = p.n;
+        p.c0 = (int)c0; p.c1 = (int)c1; p.v0 = (int)v0; p.v1 = (int)v1;
+        p.stall_at_first = (v1 - v0 == p.n);
+        // edge updates of one iteration: CN position q carries vns_pos edges from each VN position q-i in [0,L)
+        long long ce = 0;
+        for (long long q = c0 / cp; q < c1 / cp; q++)
+            for (int i = 0; i < d->dv; i++)
+                if (q - i >= 0 && q - i < L) ce += vp;
+        p.win_edges = ce + (v1 - v0) * d->dv;
+        bp_launch_window_begin(p, d->n_frames, st);
+        const int NumIt = (square && posW == 0) ? cap0 : cap;      // BP_SW.c:699-702
+        if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, st, nullptr))) return rc;
+    }
+    BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
+                  1, square ? ms : 0, square ? W - 2 : W - 2 - ms};   // posW in [ms, W-2] (BP_SW.c:846-847)
+    bp_launch_finalize(d->dv, d->dc, p, fo, st);
+    CU(cudaGetLastError());
+    if (edge_updates_host) {
+        std::vector<long long> w((size_t)p.G * p.lanes);
+        CU(cudaMemcpyAsync(w.data(), p.work, sizeof(long long) * w.size(), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        long long tot = 0;
+        for (long long x : w) tot += x;
+        *edge_updates_host = tot;
+    }
+    return 0;
+}
+
+// ---- instrumentation --------------------------------------------------------------------------------------------
+extern "C" long long scldpc_launch_count(int reset)
+{
+    long long v = g_prof.launches;
+    if (reset) g_prof.launches = 0;
+    return v;
+}
+
+// Times the CN and VN sweeps of every sample_every-th iteration with CUDA events on the launching stream.
+extern "C" int scldpc_profile_begin(int sample_every, int max_samples)
+{
+    int rc = have_device();
+    if (rc) return rc;
+    if (sample_every < 1 || max_samples < 1) return fail(SCLDPC_EINVAL, "sample_every and max_samples must be >= 1");
+    if (g_prof.ev) {
+        for (int i = 0; i < 3 * g_prof.max_samples; i++) cudaEventDestroy(g_prof.ev[i]);
+        delete[] g_prof.ev;
+        delete[] g_prof.iter_idx;
+    }
+    g_prof.ev = new cudaEvent_t[3 * (size_t)max_samples];
+    g_prof.iter_idx = new int[max_samples];
+    for (int i = 0; i < 3 * max_samples; i++) CU(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.max_samples = max_samples;
+    g_prof.n_samples = 0;
+    g_prof.sample_every = sample_every;
+    return 0;
+}
+
+// Stops sampling; returns the number of samples and, per sample, the iteration index and the two durations (ms).
+extern "C" int scldpc_profile_end(int *n_samples, int *iter_idx, float *cn_ms, float *vn_ms, int capacity)
+{
+    g_prof.sample_every = 0;
+    if (!n_samples) return fail(SCLDPC_EINVAL, "n_samples is NULL");
+    CU(cudaDeviceSynchronize());
+    int m = g_prof.n_samples < capacity ? g_prof.n_samples : capacity;
+    for (int i = 0; i < m; i++) {
+        if (iter_idx) iter_idx[i] = g_prof.iter_idx[i];
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, g_prof.ev[3 * i], g_prof.ev[3 * i + 1]));
+        CU(cudaEventElapsedTime(&b, g_prof.ev[3 * i + 1], g_prof.ev[3 * i + 2]));
+        if (cn_ms) cn_ms[i] = a;
+        if (vn_ms) vn_ms[i] = b;
+    }
+    *n_samples = m;
+    g_prof.n_samples = 0;
+    return 0;
+}
+
+// ---- host-buffer convenience entry point --------------------------------------------------------------------------
+
+// Stream-ordered allocations from the device's default pool; the pool keeps freed memory (release threshold raised
+// once), so repeated calls do not pay cudaMalloc / cudaFree.
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
+    int alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, nullptr) == cudaSuccess ? 0 : -1; }
+};
+
+static void keep_pool_memory()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+}
+
+extern "C" int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const uint8_t *erased_host, int W, int max_it,
+                                  int init_it, uint32_t flags, int32_t *iters_host, int32_t *residual_host,
+                                  int32_t *blocks_err_host, int32_t *erasures_exp_host, int32_t *blocks_err_exp_host,
+                                  int32_t *erasures_p1_host, uint8_t *vn_erased_host, int32_t *rows_host, int max_rows)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!vn_cn_host || !erased_host) return fail(SCLDPC_EINVAL, "NULL input pointer");
+    if ((rc = have_device())) return rc;
+    const size_t G = d->n_graphs, Wd = d->n_words, lanes = 64 * Wd, F = d->n_frames;
+    const size_t n = (size_t)d->L * d->vns_pos, nk = (size_t)(d->L + d->dv - 1) * d->cns_pos, E = n * d->dv;
+    const bool traj = (flags & SCLDPC_F_TRAJECTORY) && W == 0;
+    if ((flags & SCLDPC_F_TRAJECTORY) && (!rows_host || max_rows <= 0)) return fail(SCLDPC_EINVAL, "rows_host / max_rows missing");
+    keep_pool_memory();
+    DevBuf vn_cn, vn_slot, cn_edge, chan, scratch, ws, res, xbuf, rows, bytes;
+    const uint32_t kflags = flags & ~SCLDPC_F_CHAN_PACKED;
+    const size_t ws_bytes = scldpc_bp_workspace_bytes(d, kflags);
+    if (vn_cn.alloc(4 * G * E) || vn_slot.alloc(4 * G * E) || cn_edge.alloc(4 * G * nk * d->dc) || chan.alloc(8 * G * n * Wd) ||
+        scratch.alloc(4 * G * nk) || ws.alloc(ws_bytes) || res.alloc(4 * 6 * G * lanes) || xbuf.alloc(8 * G * n * Wd) ||
+        (traj && rows.alloc(4 * 3 * G * (size_t)max_rows * lanes)) || (vn_erased_host && bytes.alloc(G * F * n)))
+        return fail(SCLDPC_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStream_t st = nullptr;
+    CU(cudaMemcpyAsync(vn_cn.p, vn_cn_host, 4 * G * E, cudaMemcpyHostToDevice, st));
+    scldpc_batch_t b{static_cast<int32_t *>(vn_cn.p), static_cast<int32_t *>(vn_slot.p), static_cast<int32_t *>(cn_edge.p),
+                     static_cast<uint64_t *>(chan.p)};
+    if ((rc = scldpc_graph_build_tables(d, &b, static_cast<int32_t *>(scratch.p), st))) return rc;
+    if (flags & SCLDPC_F_CHAN_PACKED) CU(cudaMemcpyAsync(chan.p, erased_host, 8 * G * n * Wd, cudaMemcpyHostToDevice, st));
+    else if ((rc = scldpc_channel_pack_host(d, erased_host, static_cast<uint64_t *>(chan.p), st))) return rc;
+    int32_t *r = static_cast<int32_t *>(res.p);
+    scldpc_bp_out_t out{r, r + G * lanes, r + 2 * G * lanes, r + 3 * G * lanes, r + 4 * G * lanes, r + 5 * G * lanes,
+                        static_cast<uint64_t *>(xbuf.p), traj ? static_cast<int32_t *>(rows.p) : nullptr, traj ? max_rows : 0};
+    if (traj) CU(cudaMemsetAsync(rows.p, 0, 4 * 3 * G * (size_t)max_rows * lanes, st));
+    if (W == 0) rc = scldpc_bp_full(d, &b, max_it, kflags, &out, ws.p, ws_bytes, nullptr, st);
+    else rc = scldpc_bp_window(d, &b, W, max_it, init_it, kflags & ~SCLDPC_F_TRAJECTORY, &out, ws.p, ws_bytes, nullptr, st);
+    if (rc) return rc;
+    std::vector<int32_t> h(6 * G * lanes);
+    CU(cudaMemcpyAsync(h.data(), r, 4 * h.size(), cudaMemcpyDeviceToHost, st));
+    if (vn_erased_host) {
+        bits_unpack(static_cast<u64 *>(xbuf.p), static_cast<uint8_t *>(bytes.p), (int)G, (int)n, (int)Wd, (int)F, st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(vn_erased_host, bytes.p, G * F * n, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int32_t> hr;
+    if (traj) {
+        hr.resize(3 * G * (size_t)max_rows * lanes);
+        CU(cudaMemcpyAsync(hr.data(), rows.p, 4 * hr.size(), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    int32_t *dsts[6] = {iters_host, residual_host, blocks_err_host, erasures_exp_host, blocks_err_exp_host, erasures_p1_host};
+    for (int a = 0; a < 6; a++)
+        if (dsts[a])
+            for (size_t g = 0; g < G; g++)
+                memcpy(dsts[a] + g * F, h.data() + (a * G + g) * lanes, 4 * F);
+    if (traj)   // [G][max_rows][lanes][3] -> [G][n_frames][max_rows][3]
+        for (size_t g = 0; g < G; g++)
+            for (size_t f = 0; f < F; f++)
+                for (int t = 0; t < max_rows; t++)
+                    memcpy(rows_host + ((g * F + f) * max_rows + t) * 3, hr.data() + ((g * max_rows + t) * lanes + f) * 3, 12);
+    return 0;
+}

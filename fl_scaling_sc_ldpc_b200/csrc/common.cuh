@@ -1,0 +1,116 @@
+// common.cuh -- shared device helpers and the internal parameter block of the BP kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef unsigned long long u64;
+typedef ulonglong2 u128;   // one 16-byte chunk = 128 bit-sliced frames
+
+#define SCLDPC_MAX_WORDS 16
+#define SCLDPC_MAX_LANES (64 * SCLDPC_MAX_WORDS)
+
+__device__ __forceinline__ u128 make_u128(u64 a, u64 b) { u128 r; r.x = a; r.y = b; return r; }
+__device__ __forceinline__ u128 operator|(u128 a, u128 b) { return make_u128(a.x | b.x, a.y | b.y); }
+__device__ __forceinline__ u128 operator&(u128 a, u128 b) { return make_u128(a.x & b.x, a.y & b.y); }
+__device__ __forceinline__ u128 operator~(u128 a) { return make_u128(~a.x, ~a.y); }
+__device__ __forceinline__ u128 &operator|=(u128 &a, u128 b) { a.x |= b.x; a.y |= b.y; return a; }
+__device__ __forceinline__ u128 &operator&=(u128 &a, u128 b) { a.x &= b.x; a.y &= b.y; return a; }
+__device__ __forceinline__ bool nz(u128 a) { return (a.x | a.y) != 0ull; }
+__device__ __forceinline__ bool neq(u128 a, u128 b) { return ((a.x ^ b.x) | (a.y ^ b.y)) != 0ull; }
+// lanes of `m` take `a`, the others `b`
+__device__ __forceinline__ u128 sel(u128 m, u128 a, u128 b) { return make_u128((a.x & m.x) | (b.x & ~m.x), (a.y & m.y) | (b.y & ~m.y)); }
+__device__ __forceinline__ u128 zero128() { return make_u128(0ull, 0ull); }
+__device__ __forceinline__ u128 ones128() { return make_u128(~0ull, ~0ull); }
+
+// streaming (read-once) global load through the non-coherent path, no L1 allocation
+__device__ __forceinline__ u128 ld_stream(const u128 *p)
+{
+    u128 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(u128 *p, u128 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ u64 ld_cg(const u64 *p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
+
+// OR-reduce a u128 over the threads of a warp that share (threadIdx.x % chunks); chunks is a power of two <= 8
+__device__ __forceinline__ u128 warp_or_same_chunk(u128 v, int chunks)
+{
+    for (int off = chunks; off < 32; off <<= 1) {
+        v.x |= __shfl_xor_sync(0xffffffffu, v.x, off);
+        v.y |= __shfl_xor_sync(0xffffffffu, v.y, off);
+    }
+    return v;
+}
+
+// per-lane sparse counting: add 1 to cnt[base + bit] for every set bit of the chunk
+__device__ __forceinline__ void sparse_count(int *cnt, int base, u128 m)
+{
+    u64 a = m.x;
+    while (a) { int b = __ffsll((long long)a) - 1; atomicAdd(&cnt[base + b], 1); a &= a - 1; }
+    a = m.y;
+    while (a) { int b = __ffsll((long long)a) - 1; atomicAdd(&cnt[base + 64 + b], 1); a &= a - 1; }
+}
+
+// Internal parameter block (by value to every BP kernel).
+struct BpParams {
+    // dimensions
+    int dv, dc, n, nk, E, L, vns_pos, cns_pos, G, W, chunks, chunk_shift, lanes;
+    // graph + channel
+    const int32_t *vn_cn;     // [G][n][dv]
+    const int32_t *vn_slot;   // [G][n][dv]
+    const int32_t *cn_edge;   // [G][nk][dc]
+    const u128 *chan;         // [G][n][chunks]
+    // state
+    u128 *v2c;                // [G][E+1][chunks]  VN-major messages (Lji); row E is the all-zero dummy
+    u128 *c2v;                // [G][nk*dc][chunks] CN-major messages (Lij)
+    u128 *latch;              // [G][nk][chunks]    CNresolved (trajectory mode)
+    u128 *x;                  // [G][n][chunks]     a-posteriori erasures (VNerased)
+    u64 *active;              // [G][W] lanes still iterating
+    u64 *any_new;             // [G][W] lanes that resolved a VN in this iteration
+    u64 *any_er;              // [G][W] lanes with an erased VN left (in the window)
+    u64 *pos_er;              // [G][L][W] lanes with an erased VN in position p (trajectory mode)
+    unsigned *ticket;         // [G]
+    int *alive;               // [G] any active lane
+    int *alive_total;         // [1] graphs with an active lane
+    int *cnt_dvn;             // [G][lanes] newly resolved VNs of this iteration (trajectory mode)
+    int *cnt_deg1;            // [G][lanes] degree-one CNs of this iteration (trajectory mode)
+    int *pos_cnt;             // [G][L][lanes] erased VNs per position (finalisation)
+    int *pos_pairs;           // [G][L][lanes] accepted size-two stopping sets per position
+    long long *work;          // [G][lanes] edge updates (window decoder)
+    // outputs
+    int *iters;               // [G][lanes]
+    int *rows;                // [G][max_rows][lanes][3]
+    int max_rows;
+    // per-launch
+    int c0, c1, v0, v1;       // CN / VN ranges swept
+    int iter;                 // iteration index inside the current loop
+    int max_it;               // cap of the current loop
+    int first_iter;           // 1: the previous a-posteriori state is "all erased" (NumErasuresPrec = n)
+    int stall_at_first;       // 1: the stall test is meaningful at first_iter (the sweep covers all n VNs)
+    int row;                  // trajectory row written by this iteration (-1: none)
+    long long win_edges;      // edge updates of one iteration of the current sweep ranges
+};
+
+// Per-frame result pointers of the finalisation kernels.
+struct BpFinalOut {
+    int *residual, *blocks_err, *erasures_exp, *blocks_err_exp, *erasures_p1;
+    int exp_all;         // decodeBP_SW adds every position (BP_SW.c:903-907); decodeBP only the first (BP_FULL.c:1126-1131)
+    int p1_lo, p1_hi;    // positions whose erasures count towards NumErasuresP1 (BP_SW.c:846-847); empty if lo > hi
+};
+
+namespace scldpc {
+// host-side instrumentation shared by the launchers (capi.cu owns the storage)
+struct Profiler {
+    long long launches;          // kernels launched by this library since the last reset
+    int sample_every;            // 0 = off; otherwise time the sweeps of every sample_every-th iteration
+    int max_samples, n_samples;
+    cudaEvent_t *ev;             // 3 events per sample: before CN sweep, between, after VN sweep
+    int *iter_idx;
+};
+extern Profiler g_prof;
+}  // namespace scldpc

@@ -1,0 +1,149 @@
+/*
+ * scldpc.h -- C ABI of libscldpc.so, the B200 (sm_100a) Monte-Carlo decoding engine for (dv,dc)-regular
+ * SC-LDPC codes over the BEC.
+ *
+ * The reference (rsokolovskii/fl_scaling_sc_ldpc) has no FFI of its own: its hot path is reached through C
+ * functions operating on file-scope tables and through Python callables.  Each entry point below names the
+ * reference interface it replaces (file:line; abbreviations as in SURVEY.md):
+ *   BP_FULL.c = simulators_sc_ldpc/bp_decoding/SC_LDPC_Simulator_BPDecoder_BEC_full_BP_LimIter_OlmosRandomEnsemble.c
+ *   BP_SW.c   = simulators_sc_ldpc/bp_decoding/SC_LDPC_Simulator_BPDecoder_BEC_SlidingWindow_LimIter_OlmosRandomEnsemble.c
+ *   BP_TRAJ.c = simulators_sc_ldpc/bp_decoding/trajectories_SC_LDPC_Simulator_BPDecoder_BEC_full_BP_OlmosRandomEnsemble.c
+ *   PD.py     = simulators_sc_ldpc/peeling_decoding/peeling_decoding.py
+ *   SC.py     = simulators_sc_ldpc/peeling_decoding/sc_ldpc.py
+ *
+ * Conventions
+ *  - Plain C types only.  Pointers named *_dev are device pointers (owned by the caller, e.g. a torch
+ *    tensor's data_ptr()); pointers named *_host are host pointers.  `stream` is a cudaStream_t passed as
+ *    void* (NULL = default stream).  Every function returns 0 on success and a negative SCLDPC_E* code on
+ *    failure; scldpc_last_error() returns a thread-local message.  There is NO CPU fallback: without a CUDA
+ *    device every compute entry point fails with SCLDPC_ECUDA.
+ *  - A batch holds n_graphs independent graph realisations; each graph decodes 64*n_words frames at once,
+ *    bit-sliced: bit b of 64-bit word w of a node is that node's value in frame 64*w+b of the graph.
+ *    n_words must be a power of two in [2,16].
+ *  - M := vns_pos = VNs per position (paper / Python convention); the C files' Def_M equals cns_pos.
+ *    n = L*vns_pos VNs, nk = (L+dv-1)*cns_pos CNs, E = n*dv edges per graph.
+ */
+#ifndef SCLDPC_H
+#define SCLDPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLDPC_OK 0
+#define SCLDPC_EINVAL (-1)   /* bad argument                       */
+#define SCLDPC_ECUDA (-2)    /* CUDA runtime error / no device     */
+#define SCLDPC_ENOMEM (-3)   /* workspace too small                */
+#define SCLDPC_EGRAPH (-4)   /* malformed graph (CN degree > dc..) */
+
+/* decoder flags */
+#define SCLDPC_F_TERMINATED 1u   /* is_term (BP_TRAJ.c:901): 0 = truncated, tail CNs always send erasures      */
+#define SCLDPC_F_TRAJECTORY 2u   /* record (deg_1_iter, dVNs, first erased position) per iteration              */
+#define SCLDPC_F_SQUARE 4u       /* window decoder: square window (BP_SW.c) instead of classical (BP_FULL.c)    */
+#define SCLDPC_F_EXP_ALL 8u      /* expurgated statistics over all positions (decodeBP_SW) instead of the first */
+#define SCLDPC_F_CHAN_PACKED 16u /* scldpc_decode_host: erased_host is already bit-sliced, uint64 [G][n][n_words] */
+
+typedef struct {
+    int32_t dv, dc;        /* variable / check node degree (Def_dv, Def_dc; BP_FULL.c:22-23)                */
+    int32_t L;             /* chain length (Def_L)                                                          */
+    int32_t vns_pos;       /* VNs per position (Def_VNsPos = M)                                             */
+    int32_t cns_pos;       /* CNs per position (Def_CNsPos = Def_M); vns_pos*dv must equal cns_pos*dc       */
+    int32_t n_graphs;      /* graph realisations in the batch                                               */
+    int32_t n_words;       /* 64-bit lane words per node; frames per graph = 64*n_words                     */
+    int32_t n_frames;      /* valid frames per graph (<= 64*n_words); remaining lanes are ignored           */
+} scldpc_dims_t;
+
+/* Device buffers of a batch.  Sizes in elements, G = n_graphs, W = n_words, n/nk/E per graph as above. */
+typedef struct {
+    const int32_t *vn_cn_dev;   /* [G][n][dv]   CN index of edge i of VN v (VNdegree[v][1+i], BP_FULL.c:87)    */
+    int32_t *vn_slot_dev;       /* [G][n][dv]   c*dc+j: slot of that edge in its CN row (built by the library) */
+    int32_t *cn_edge_dev;       /* [G][nk][dc]  v*dv+i of the j-th edge of CN c in VN order, or E if absent    */
+    const uint64_t *chan_dev;   /* [G][n][W]    1 = erased by the channel (LLRsChannel, BP_FULL.c:91)          */
+} scldpc_batch_t;
+
+/* Per-frame results, all int32 [G][64*W] on the device (lane = 64*w+b). */
+typedef struct {
+    int32_t *iters_dev;           /* iterations executed (full BP) / total over windows (window decoder)        */
+    int32_t *residual_dev;        /* NumErasures returned by decodeBP / decodeBP_SW                             */
+    int32_t *blocks_err_dev;      /* *num_blocks_err                                                           */
+    int32_t *erasures_exp_dev;    /* *num_erasures_exp                                                         */
+    int32_t *blocks_err_exp_dev;  /* *num_blocks_err_exp                                                       */
+    int32_t *erasures_p1_dev;     /* *NumErasuresP1 (window decoder only; may be NULL)                         */
+    uint64_t *erased_dev;         /* [G][n][W] VNerased after decoding (BP_FULL.c:94)                          */
+    int32_t *rows_dev;            /* [G][max_rows][64*W][3] trajectory rows (deg1, dVNs, first_pos) or NULL     */
+    int32_t max_rows;
+} scldpc_bp_out_t;
+
+const char *scldpc_last_error(void);
+int scldpc_version(void);
+/* number of CUDA devices visible (0 => every compute call fails); never throws */
+int scldpc_device_count(void);
+
+/* ---- graph tables ------------------------------------------------------------------------------------ */
+/* Builds vn_slot / cn_edge from vn_cn on the device, CN rows in the order generate_code appends them
+ * (BP_FULL.c:1702-1716).  Replaces the CNdegree half of generate_code.  scratch_dev: int32 [G][nk]. */
+int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_batch_t *b, int32_t *scratch_dev, void *stream);
+
+/* On-device ensemble generation: the "Olmos random ensemble" of generate_code (BP_FULL.c:1656-1761) /
+ * SC.gen_slots (SC.py:33-56): an independent uniform socket permutation per CN position.  Graph g of the batch
+ * is realisation first_graph_id+g of stream `seed` (Philox4x32-10), independent of the batch / GPU layout.
+ * tail_biting != 0 gives SC.gen_slots_tail_biting (SC.py:41-45, nk = L*cns_pos).  scratch_dev: uint64
+ * [G][L+dv-1][cns_pos*dc] sort keys. */
+int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
+                          uint64_t first_graph_id, int tail_biting, void *stream);
+size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting);
+
+/* ---- channel ------------------------------------------------------------------------------------------ */
+/* BEC realisations, bit-sliced (channel_doped, BP_FULL.c:1547-1574; PD.py:154, :174-192).  Frame f of graph g
+ * uses Philox stream (seed, first_graph_id+g, f).  Hard doping: all VNs of positions doped_pos_host[] known.
+ * Soft doping: the first soft_count_host[p] VNs of position soft_pos_host[p] known (int(alpha*M), PD.py:177). */
+int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                            int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
+                            uint64_t seed, uint64_t first_graph_id, void *stream);
+
+/* Packs byte-per-VN erasure patterns (host, [G][n_frames][n], 1 = erased) into chan_dev. */
+int scldpc_channel_pack_host(const scldpc_dims_t *d, const uint8_t *erased_host, uint64_t *chan_dev, void *stream);
+
+/* ---- decoders ----------------------------------------------------------------------------------------- */
+size_t scldpc_bp_workspace_bytes(const scldpc_dims_t *d, uint32_t flags);
+
+/* Full flooding BP over the BEC -- decodeBP (BP_FULL.c:900-1140, BP_TRAJ.c:901-1151).  max_it <= 0 means
+ * unlimited (run until every frame has stalled or finished).  *iters_launched_host (optional) receives the number of
+ * flooding iterations launched for the batch. */
+int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
+                   const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                   int *iters_launched_host, void *stream);
+
+/* Sliding-window BP -- decodeBP_SW (square: BP_SW.c:628-912; classical: BP_FULL.c:627-897).  init_it <= 0 means
+ * max_it (BP_SW.c:2099-2102).  Without SCLDPC_F_TERMINATED the CN window is clipped at L*cns_pos (derived
+ * non-terminated mode). */
+int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                     const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                     int64_t *edge_updates_host, void *stream);
+
+/* Reference-facing convenience entry point with HOST buffers (what a maintainer would call in place of
+ * generate_code + channel_doped + decodeBP, BP_FULL.c:2122-2133): uploads vn_cn_host [G][n][dv] and erased_host
+ * [G][n_frames][n], decodes, and downloads the per-frame results (int32 [G][n_frames] each; any may be NULL) and
+ * optionally the erased bitmaps (uint8 [G][n_frames][n]).  W == 0 selects full BP, W > 0 the window decoder.
+ * All device memory is allocated and released inside the call. */
+int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const uint8_t *erased_host, int W, int max_it,
+                       int init_it, uint32_t flags, int32_t *iters_host, int32_t *residual_host,
+                       int32_t *blocks_err_host, int32_t *erasures_exp_host, int32_t *blocks_err_exp_host,
+                       int32_t *erasures_p1_host, uint8_t *vn_erased_host, int32_t *rows_host, int max_rows);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------ */
+/* kernels launched by the library since the last reset */
+long long scldpc_launch_count(int reset);
+/* Sampled CUDA-event timing of the two sweeps of every sample_every-th flooding iteration (on the launching
+ * stream).  profile_end synchronises the device and returns per sample the iteration index and the CN / VN sweep
+ * durations in milliseconds. */
+int scldpc_profile_begin(int sample_every, int max_samples);
+int scldpc_profile_end(int *n_samples, int *iter_idx, float *cn_ms, float *vn_ms, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCLDPC_H */

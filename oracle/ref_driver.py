@@ -134,12 +134,15 @@ class RefLib:
         return self.LLRsChannel.astype(np.uint8).copy()
 
     # ---- decoders ---------------------------------------------------------------------------------
-    def decode_bp(self, max_it: int, is_term: int = 1, W: int = 0) -> dict:
+    def decode_bp(self, max_it: int, is_term: int = 1, W: int = 0, exp_positions: int | None = None) -> dict:
         """Reference ``decodeBP``.  For the "traj" variant the per-iteration rows are parsed from the text the
-        reference writes (``iter deg1 dVNs first_erased_pos``)."""
+        reference writes (``iter deg1 dVNs first_erased_pos``).  ``exp_positions`` is the ``L`` argument, which the
+        function uses only as the range of its post-decoding expurgation scan (BP_FULL.c:1075); passing 0 skips
+        that scan (used when timing the iterations of capped runs, where it would be quadratic in the erasures)."""
         self._g("MaxNumIt").value = max_it
         nb, ne, nbe = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
-        args = [ctypes.c_int(x) for x in (self.n, self.nk, self.L, W, self.vns_pos, self.cns_pos)]
+        Larg = self.L if exp_positions is None else exp_positions
+        args = [ctypes.c_int(x) for x in (self.n, self.nk, Larg, W, self.vns_pos, self.cns_pos)]
         args += [ctypes.byref(nb), ctypes.byref(ne), ctypes.byref(nbe)]
         rows = None
         if self.variant == "traj":

@@ -1,0 +1,147 @@
+"""GPU parity tests: the CUDA decoders (through the C ABI) against the CPU oracle and the committed golden vectors,
+bit-exact on every output the reference produces: iterations executed, NumErasures, VNerased, block / expurgated
+statistics and the per-iteration trajectory rows."""
+import numpy as np
+import pytest
+
+import fl_scaling_sc_ldpc_b200 as eng
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("iters", "residual", "blocks_err", "erasures_exp", "blocks_err_exp")
+
+
+def make_batch(dv, dc, L, M, graphs, chan, n_words=None):
+    ens = eng.Ensemble(dv, dc, L, M)
+    G, F, _ = chan.shape
+    fb = eng.FrameBatch(ens, G, F, n_words)
+    fb.set_graphs(np.stack([g.vn_cn for g in graphs]))
+    fb.set_erasures(chan)
+    return fb
+
+
+def check_bp(res, ref, rows=False):
+    for k in KEYS:
+        assert (getattr(res, k) == ref[k]).all(), (k, getattr(res, k), ref[k])
+    assert (res.erased() == ref["erased"]).all()
+    if rows:
+        G, F = ref["iters"].shape
+        for g in range(G):
+            for f in range(F):
+                k = min(ref["iters"][g, f], res.rows.shape[2])
+                assert (res.rows[g, f, :k] == ref["rows"][g, f, :k]).all(), (g, f)
+
+
+@pytest.mark.parametrize("dv,dc,L,M", [(4, 8, 10, 50), (3, 6, 10, 48), (5, 10, 12, 40), (4, 8, 6, 16), (4, 8, 20, 128)])
+def test_full_bp_matches_oracle(dv, dc, L, M):
+    eps = [0.30, 0.42, 0.46, 0.50, 0.56] if dv != 3 else [0.3, 0.38, 0.42, 0.47]
+    graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=70, eps_list=eps, seed=1000 + L + M, doped_every=9)
+    fb = make_batch(dv, dc, L, M, graphs, chan)
+    for is_term in (True, False):
+        for cap in (0, 7, 1):
+            ref = util.oracle_bp(graphs, chan, cap, int(is_term), max_rows=64)
+            res = eng.decode_bp_full(fb, cap, is_term)
+            check_bp(res, ref)
+            rest = eng.decode_bp_full(fb, cap, is_term, trajectory=True, max_rows=64)
+            check_bp(rest, ref, rows=True)
+
+
+def test_full_bp_lane_words_and_ragged_frames():
+    """every supported lane-word count, frame counts that do not fill the last word, and zero frames"""
+    dv, dc, L, M = 4, 8, 8, 32
+    for n_words, F in ((2, 1), (2, 128), (4, 130), (8, 300), (16, 700)):
+        graphs, chan, _ = util.random_case(dv, dc, L, M, G=1, F=F, eps_list=[0.44, 0.5], seed=77 + F)
+        fb = make_batch(dv, dc, L, M, graphs, chan, n_words)
+        ref = util.oracle_bp(graphs, chan, 0, 1, max_rows=48)
+        check_bp(eng.decode_bp_full(fb, 0, True, trajectory=True, max_rows=48), ref, rows=True)
+    fb = eng.FrameBatch(eng.Ensemble(dv, dc, L, M), 1, 0, 2)
+    fb.set_graphs(graphs[0].vn_cn[None])
+    r = eng.decode_bp_full(fb, 0, True)
+    assert r.iters.shape == (1, 0)
+
+
+def test_full_bp_extreme_channels():
+    """all-known, all-erased and single-erasure patterns"""
+    dv, dc, L, M = 4, 8, 6, 16
+    graphs, chan, _ = util.random_case(dv, dc, L, M, G=1, F=5, eps_list=[0.4], seed=5)
+    chan[0, 0] = 0
+    chan[0, 1] = 1
+    chan[0, 2] = 0; chan[0, 2, 17] = 1
+    chan[0, 3] = 1; chan[0, 3, : M] = 0
+    fb = make_batch(dv, dc, L, M, graphs, chan)
+    for is_term in (True, False):
+        ref = util.oracle_bp(graphs, chan, 0, int(is_term), max_rows=32)
+        check_bp(eng.decode_bp_full(fb, 0, is_term, trajectory=True, max_rows=32), ref, rows=True)
+
+
+@pytest.mark.parametrize("dv,dc,L,M", [(4, 8, 10, 50), (3, 6, 10, 48), (4, 8, 14, 64)])
+def test_window_bp_matches_oracle(dv, dc, L, M):
+    eps = [0.35, 0.44, 0.47, 0.52] if dv != 3 else [0.3, 0.38, 0.42]
+    graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=40, eps_list=eps, seed=2000 + L + M, doped_every=7)
+    fb = make_batch(dv, dc, L, M, graphs, chan)
+    for square in (True, False):
+        for is_term in (True, False):
+            for (W, cap, init) in ((3, 0, 0), (4, 4, 12), (5, 2, 0), (2, 1, 1), (L + 4, 3, 0)):
+                ref = util.oracle_sw(graphs, chan, W, cap, init if square else 0, int(square), int(is_term))
+                res = eng.decode_bp_window(fb, W, cap, init if square else 0, square, is_term)
+                for k in KEYS + ("erasures_p1",):
+                    assert (getattr(res, k) == ref[k]).all(), (square, is_term, W, cap, init, k)
+                assert (res.erased() == ref["erased"]).all()
+
+
+@pytest.mark.parametrize("path", util.golden_files(), ids=lambda p: p.split("bp_golden_")[-1])
+def test_against_golden_vectors(path):
+    """outputs of the compiled reference itself (tests/golden/make_golden.py)"""
+    z, d = util.load_golden(path)
+    ens = eng.Ensemble(d["dv"], d["dc"], d["L"], d["vns_pos"])
+    fb = eng.FrameBatch(ens, d["G"], d["F"]).set_graphs(z["vn_cn"]).set_erasures(z["chan"])
+    for is_term in (1, 0):
+        for cap in (100000, 5, 1):
+            key = f"bp_t{is_term}_c{cap}"
+            r = eng.decode_bp_full(fb, cap, bool(is_term), trajectory=True, max_rows=64)
+            st = z[key + "_stats"]
+            got = np.stack([r.iters, r.residual, r.blocks_err, r.erasures_exp, r.blocks_err_exp], axis=-1)
+            assert (got == st).all(), key
+            assert (r.erased() == util.unpack_erased(z[key + "_erased"], d["n"])).all(), key
+            for g in range(d["G"]):
+                for f in range(d["F"]):
+                    k = min(64, st[g, f, 0])
+                    assert (r.rows[g, f, :k] == z[key + "_rows"][g, f, :k]).all(), key
+    for (W, cap, init) in ((3, 100000, 0), (4, 4, 12), (5, 2, 0), (2, 1, 1)):
+        for square in (1, 0):
+            key = f"sw_s{square}_W{W}_c{cap}_i{init}"
+            r = eng.decode_bp_window(fb, W, cap, init if square else 0, bool(square), True)
+            got = np.stack([r.residual, r.erasures_p1, r.blocks_err, r.erasures_exp, r.blocks_err_exp], axis=-1)
+            assert (got == z[key + "_stats"]).all(), key
+            assert (r.erased() == util.unpack_erased(z[key + "_erased"], d["n"])).all(), key
+
+
+def test_host_buffer_entry_point():
+    """scldpc_decode_host: host graph + host erasure bytes in, per-frame results out"""
+    dv, dc, L, M = 4, 8, 10, 50
+    graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=33, eps_list=[0.4, 0.47, 0.53], seed=31)
+    vn_cn = np.stack([g.vn_cn for g in graphs])
+    ens = eng.Ensemble(dv, dc, L, M)
+    ref = util.oracle_bp(graphs, chan, 0, 1, max_rows=40)
+    o = eng.decode_host(ens, vn_cn, chan, trajectory=True, max_rows=40, want_erased=True)
+    for k in KEYS:
+        assert (o[k] == ref[k]).all(), k
+    assert (o["erased"] == ref["erased"]).all()
+    for g in range(2):
+        for f in range(33):
+            k = min(40, ref["iters"][g, f])
+            assert (o["rows"][g, f, :k] == ref["rows"][g, f, :k]).all()
+    ref = util.oracle_sw(graphs, chan, 4, 3, 10, 1, 1)
+    o = eng.decode_host(ens, vn_cn, chan, W=4, max_it=3, init_it=10, want_erased=True)
+    for k in KEYS + ("erasures_p1",):
+        assert (o[k] == ref[k]).all(), k
+    assert (o["erased"] == ref["erased"]).all()
+
+
+def test_malformed_graph_is_rejected():
+    ens = eng.Ensemble(4, 8, 6, 16)
+    fb = eng.FrameBatch(ens, 1, 4)
+    bad = np.zeros((1, ens.n, 4), np.int32)          # every edge on CN 0
+    with pytest.raises(eng.ScldpcError):
+        fb.set_graphs(bad)
