@@ -380,6 +380,7 @@ def run_ours(args):
 
 
 def main():
+    global N_WORDS, FRAMES_PER_GRAPH, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -389,7 +390,11 @@ def main():
     ap.add_argument("--graphs-per-eps", type=int, default=1)
     ap.add_argument("--sample-iters", type=int, default=10, help="reference arm: flooding iterations per sampled frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-words", type=int, default=N_WORDS, help="64-bit lane words per node (frames per graph / 64)")
     args = ap.parse_args()
+    N_WORDS = args.n_words
+    FRAMES_PER_GRAPH = 64 * N_WORDS
+    WORKLOAD = WORKLOAD.replace("512 frames", f"{FRAMES_PER_GRAPH} frames")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

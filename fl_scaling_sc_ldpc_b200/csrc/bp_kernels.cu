@@ -98,27 +98,6 @@ __global__ void bp_window_begin_kernel(BpParams p, int n_frames)
 // ------------------------------------------------------------------------------------------------------------
 // check-node sweep
 // ------------------------------------------------------------------------------------------------------------
-template <int DC>
-__device__ __forceinline__ void load_row(const int32_t *row, int (&e)[DC])
-{
-    if constexpr (DC % 4 == 0) {
-#pragma unroll
-        for (int q = 0; q < DC / 4; q++) {
-            int4 t = __ldg(reinterpret_cast<const int4 *>(row) + q);
-            e[4 * q] = t.x; e[4 * q + 1] = t.y; e[4 * q + 2] = t.z; e[4 * q + 3] = t.w;
-        }
-    } else if constexpr (DC % 2 == 0) {
-#pragma unroll
-        for (int q = 0; q < DC / 2; q++) {
-            int2 t = __ldg(reinterpret_cast<const int2 *>(row) + q);
-            e[2 * q] = t.x; e[2 * q + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < DC; q++) e[q] = __ldg(row + q);
-    }
-}
-
 template <int DC, bool TRAJ, bool FREEZE>
 __global__ void __launch_bounds__(256) bp_cn_sweep_kernel(BpParams p)
 {
@@ -455,9 +434,8 @@ static int num_sms()
 static dim3 sweep_grid(long long items, int G, int block, int blocks_per_sm)
 {
     long long need = (items + block - 1) / block;
-    long long cap = (long long)num_sms() * blocks_per_sm;
-    long long per_graph = (cap + G - 1) / G;
-    if (per_graph < 1) per_graph = 1;
+    long long per_graph = (long long)num_sms() * blocks_per_sm;   // each graph can fill the machine on its own
+    (void)G;
     long long gx = need < per_graph ? need : per_graph;
     if (gx < 1) gx = 1;
     return dim3((unsigned)gx, (unsigned)G, 1);

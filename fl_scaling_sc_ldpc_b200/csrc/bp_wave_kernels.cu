@@ -1,0 +1,368 @@
+// bp_wave_kernels.cu -- full flooding BP with wave tracking (sm_100a).
+//
+// Decoding an SC-LDPC code is a travelling wave: after a short transient only the ~10 positions around each wave
+// front change, positions behind a front are resolved and positions ahead of it sit at a fixed point of the local
+// rule.  The reference sweeps all L(+dv-1) positions in every iteration (BP_FULL.c:943,985,1009).  Here a sweep
+// visits a position only if one of its inputs changed since it was last computed -- which leaves every message,
+// every decision and every counter bit-identical, because a node whose inputs did not change recomputes its old
+// outputs:
+//   * a VN's outgoing messages are a function of its state (x, y): x = a-posteriori erasure, y = "some outgoing
+//     message is an erasure" (incoming Lij only go 1->0, so the state walks 4 erased -> 3 erased -> <=2 erased and
+//     the outgoing messages change exactly when (x, y) changes).  The VN sweep compares (x, y) with the stored
+//     planes and stamps its position when any active frame changed;
+//   * CN position p is swept in iteration t iff a VN position in [p-dv+1, p] was stamped in iteration t-1;
+//   * VN position q is swept in iteration t iff a CN position in [q, q+dv-1] was swept in iteration t.
+// The lists are rebuilt on the device by the last block of each VN sweep.  Messages of VNs that did not change
+// are not written back.  Besides doing less work, the live region (a few tens of MB) stays resident in the 126 MB
+// L2 across iterations, so most of its traffic never reaches HBM.
+//
+// Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
+#include "common.cuh"
+
+namespace scldpc {
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bp_wave_init_kernel(BpParams p)
+{
+    const int g = blockIdx.x;
+    const int ncp = p.L + p.dv - 1;
+    for (int i = threadIdx.x; i < ncp; i += blockDim.x) p.cn_list[g * ncp + i] = i;
+    for (int i = threadIdx.x; i < p.L; i += blockDim.x) {
+        p.vn_list[g * p.L + i] = i;
+        p.vn_stamp[g * p.L + i] = -1;
+    }
+    for (int i = threadIdx.x; i < p.L * p.W; i += blockDim.x) p.pos_er_new[(size_t)g * p.L * p.W + i] = 0;
+    if (threadIdx.x == 0) {
+        p.n_list[2 * g] = p.cn_pos_lim;
+        p.n_list[2 * g + 1] = p.L;
+        p.swept[2 * g] = 0;
+        p.swept[2 * g + 1] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// check-node sweep over the listed positions
+// ------------------------------------------------------------------------------------------------------------
+template <int DC, bool TRAJ>
+__global__ void __launch_bounds__(256) bp_cn_wave_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
+    if (TRAJ) {
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
+        __syncthreads();
+    }
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const u128 *__restrict__ v2c = p.v2c + (size_t)g * (p.E + 1) * ch;
+    u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * DC * ch;
+    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const int *__restrict__ list = p.cn_list + g * (p.L + p.dv - 1);
+
+    if (nz(act)) {
+        const int ipp = p.cns_pos << p.chunk_shift;                 // work items per position
+        const int items = ld_cg(p.n_list + 2 * g) * ipp;
+        const int stride = gridDim.x * blockDim.x;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+            const int ent = idx / ipp, off = idx - ent * ipp;
+            const int c = __ldg(list + ent) * p.cns_pos + (off >> p.chunk_shift);
+            int e[DC];
+            load_row<DC>(cn_edge + (size_t)c * DC, e);
+            u128 in[DC];
+#pragma unroll
+            for (int j = 0; j < DC; j++) in[j] = ld_stream(v2c + (size_t)e[j] * ch + k);
+            u128 out[DC];
+            u128 acc = zero128();
+#pragma unroll
+            for (int j = 0; j < DC; j++) { out[j] = acc; acc |= in[j]; }
+            acc = zero128();
+#pragma unroll
+            for (int j = DC - 1; j >= 0; j--) { out[j] |= acc; acc |= in[j]; }
+            u128 *dst = c2v + ((size_t)c * DC) * ch + k;
+#pragma unroll
+            for (int j = 0; j < DC; j++) dst[(size_t)j * ch] = out[j];
+            if (TRAJ) {
+                u128 one = zero128(), two = zero128();
+#pragma unroll
+                for (int j = 0; j < DC; j++) {
+                    if (e[j] != p.E) { u128 z = ~out[j]; two |= one & z; one |= z; }
+                }
+                u128 *lp = p.latch + ((size_t)g * p.nk + c) * ch + k;
+                const u128 lat = *lp;
+                const u128 cnt = one & ~two & ~lat & act;
+                const u128 nl = lat | (one & act);
+                if (neq(nl, lat)) *lp = nl;
+                if (nz(cnt)) sparse_count(s_cnt, k * 128, cnt);
+            }
+        }
+    }
+    if (TRAJ) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + g * p.lanes + i, s_cnt[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// end of an iteration (last block of the VN sweep): retire frames, rebuild the position lists
+// ------------------------------------------------------------------------------------------------------------
+template <bool TRAJ>
+__device__ void bp_wave_retire(const BpParams &p, int g)
+{
+    __shared__ u64 s_stop[SCLDPC_MAX_WORDS], s_act[SCLDPC_MAX_WORDS];
+    __shared__ int s_alive;
+    __shared__ unsigned char s_chg[1024 + 16], s_cn[1024 + 16];
+    const int L = p.L, W = p.W, ncp = L + p.dv - 1;
+    const int n_vn = p.n_list[2 * g + 1];
+    if (threadIdx.x == 0) s_alive = 0;
+    // positions swept in this iteration publish their "erased VN left" words
+    for (int i = threadIdx.x; i < n_vn * W; i += blockDim.x) {
+        const int pos = p.vn_list[g * L + i / W], w = i % W;
+        const size_t o = ((size_t)g * L + pos) * W + w;
+        p.pos_er[o] = ld_cg(p.pos_er_new + o);
+        p.pos_er_new[o] = 0;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        u64 er = 0;
+        for (int q = 0; q < L; q++) er |= p.pos_er[((size_t)g * L + q) * W + w];
+        const u64 a = p.active[g * W + w];
+        const u64 nw = ld_cg(p.any_new + g * W + w);
+        u64 stop = a & ~er;                                   // NumErasures == 0
+        stop |= a & ~nw;                                      // NumErasures == NumErasuresPrec (first iteration: Prec = n)
+        if (p.iter + 1 >= p.max_it) stop = a;                 // while (iter < MaxNumIt)
+        s_stop[w] = stop;
+        s_act[w] = a;
+        const u64 left = a & ~stop;
+        p.active[g * W + w] = left;
+        p.any_new[g * W + w] = 0;
+        if (left) s_alive = 1;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_stop[w] >> b) & 1ull) p.iters[g * p.lanes + l] += p.iter + 1;
+        if (TRAJ) {
+            const int dvn = ld_cg(p.cnt_dvn + g * p.lanes + l);
+            const int d1 = ld_cg(p.cnt_deg1 + g * p.lanes + l);
+            p.cnt_dvn[g * p.lanes + l] = 0;
+            p.cnt_deg1[g * p.lanes + l] = 0;
+            if (((s_act[w] >> b) & 1ull) && p.row >= 0 && p.row < p.max_rows) {
+                int first = L;
+                for (int q = 0; q < L; q++)
+                    if ((p.pos_er[((size_t)g * L + q) * W + w] >> b) & 1ull) { first = q; break; }
+                int *r = p.rows + (((size_t)g * p.max_rows + p.row) * p.lanes + l) * 3;
+                r[0] = d1; r[1] = dvn; r[2] = first;
+            }
+        }
+    }
+    // lists of the next iteration
+    for (int q = threadIdx.x; q < L; q += blockDim.x) s_chg[q] = (ld_cg(p.vn_stamp + g * L + q) == p.iter);
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncp; c += blockDim.x) {
+        unsigned char any = 0;
+        if (c < p.cn_pos_lim)
+            for (int i = 0; i < p.dv; i++)
+                if (c - i >= 0 && c - i < L && s_chg[c - i]) any = 1;
+        s_cn[c] = any;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nc = 0, nv = 0;
+        for (int c = 0; c < ncp; c++)
+            if (s_cn[c]) p.cn_list[g * ncp + nc++] = c;
+        for (int q = 0; q < L; q++) {
+            bool any = false;
+            for (int i = 0; i < p.dv; i++) any |= (s_cn[q + i] != 0);
+            if (any) p.vn_list[g * L + nv++] = q;
+        }
+        p.swept[2 * g] += p.n_list[2 * g];
+        p.swept[2 * g + 1] += n_vn;
+        p.n_list[2 * g] = nc;
+        p.n_list[2 * g + 1] = nv;
+        p.ticket[g] = 0;
+        if (!s_alive) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// variable-node sweep over the listed positions
+// ------------------------------------------------------------------------------------------------------------
+template <int DV, bool TRAJ>
+__global__ void __launch_bounds__(256) bp_vn_wave_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
+    __shared__ u64 s_new[SCLDPC_MAX_WORDS];
+    __shared__ int s_last;
+    if (TRAJ)
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
+    __syncthreads();
+
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const bool lane_work = nz(act);
+    u128 acc_new = zero128();
+    const u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * p.dc * ch;
+    u128 *__restrict__ v2c = p.v2c + (size_t)g * (p.E + 1) * ch;
+    const u128 *__restrict__ chan = p.chan + (size_t)g * p.n * ch;
+    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u128 *__restrict__ y = p.y + (size_t)g * p.n * ch;
+    const int32_t *__restrict__ vn_slot = p.vn_slot + (size_t)g * p.n * DV;
+    const int *__restrict__ list = p.vn_list + g * p.L;
+
+    const int ipp = p.vns_pos << p.chunk_shift;
+    const int items = ld_cg(p.n_list + 2 * g + 1) * ipp;
+    const int stride = gridDim.x * blockDim.x;
+    // the trip count is warp-uniform (the shuffle below needs the whole warp): bound by the warp's first item
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
+        const int idx = base + (threadIdx.x & 31);
+        const bool work = lane_work && idx < items;
+        u128 changed = zero128(), xn = zero128(), yn = zero128(), xo = zero128(), yo = zero128();
+        u128 out[DV];
+        int v = 0, pos = 0;
+        if (work) {
+            const int ent = idx / ipp, off = idx - ent * ipp;
+            pos = __ldg(list + ent);
+            v = pos * p.vns_pos + (off >> p.chunk_shift);
+            int s[DV];
+            load_row<DV>(vn_slot + (size_t)v * DV, s);
+            u128 in[DV];
+#pragma unroll
+            for (int i = 0; i < DV; i++) in[i] = ld_stream(c2v + (size_t)s[i] * ch + k);
+            const u128 cv = ld_stream(chan + (size_t)v * ch + k);
+            u128 xdet;
+            if (p.first_iter) { xo = ones128(); xdet = cv; yo = cv; }      // Lji starts at the channel value
+            else { xo = x[(size_t)v * ch + k]; xdet = xo; yo = y[(size_t)v * ch + k]; }
+            u128 acc = cv;
+#pragma unroll
+            for (int i = 0; i < DV; i++) { out[i] = acc; acc &= in[i]; }
+            xn = acc;
+            acc = ones128();
+#pragma unroll
+            for (int i = DV - 1; i >= 0; i--) { out[i] &= acc; acc &= in[i]; }
+#pragma unroll
+            for (int i = 0; i < DV; i++) yn |= out[i];
+            changed = make_u128(((xn.x ^ xdet.x) | (yn.x ^ yo.x)) & act.x, ((xn.y ^ xdet.y) | (yn.y ^ yo.y)) & act.y);
+        }
+        // a VN's row is rewritten when any of its chunks changed (the ch adjacent threads hold one VN)
+        unsigned flag = nz(changed) ? 1u : 0u;
+        for (int o = 1; o < ch; o <<= 1) flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+        if (work) {
+            if (p.first_iter || flag) {
+                u128 *dst = v2c + ((size_t)v * DV) * ch + k;
+#pragma unroll
+                for (int i = 0; i < DV; i++) dst[(size_t)i * ch] = out[i];
+            }
+            if (p.first_iter || neq(xn, xo)) x[(size_t)v * ch + k] = xn;
+            if (p.first_iter || neq(yn, yo)) y[(size_t)v * ch + k] = yn;
+            if (nz(changed)) {
+                int *st = p.vn_stamp + g * p.L + pos;
+                if (ld_cg(st) != p.iter) *st = p.iter;
+            }
+            const u128 newly = xo & ~xn & act;
+            acc_new |= newly;
+            if (TRAJ && nz(newly)) sparse_count(s_cnt, k * 128, newly);
+            const u128 er = xn & act;
+            if (nz(er)) {
+                u64 *pe = p.pos_er_new + ((size_t)g * p.L + pos) * p.W + 2 * k;
+                if (er.x & ~ld_cg(pe)) atomicOr(pe, er.x);
+                if (er.y & ~ld_cg(pe + 1)) atomicOr(pe + 1, er.y);
+            }
+        }
+    }
+    acc_new = warp_or_same_chunk(acc_new, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
+        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
+    }
+    if (TRAJ)
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(p.cnt_dvn + g * p.lanes + i, s_cnt[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        bp_wave_retire<TRAJ>(p, g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+template <typename K>
+static int resident_blocks(K kernel, int block)
+{
+    int occ = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 2;
+    return occ * (sms > 0 ? sms : 148);
+}
+
+template <int DV, int DC>
+static void launch_wave_iteration(const BpParams &p, bool traj, cudaStream_t st, int waves)
+{
+    const int block = 256;
+    static int res_cn[2] = {0, 0}, res_vn[2] = {0, 0};
+    if (!res_cn[0]) {
+        res_cn[0] = resident_blocks(bp_cn_wave_kernel<DC, false>, block);
+        res_cn[1] = resident_blocks(bp_cn_wave_kernel<DC, true>, block);
+        res_vn[0] = resident_blocks(bp_vn_wave_kernel<DV, false>, block);
+        res_vn[1] = resident_blocks(bp_vn_wave_kernel<DV, true>, block);
+    }
+    // every graph gets enough blocks to fill the machine on its own (`waves` x the resident block count): blocks
+    // of finished graphs return at once, so the graphs still decoding always have the whole GPU
+    auto grid = [&](int resident, long long items_per_graph) {
+        long long need = (items_per_graph + block - 1) / block;
+        long long per_graph = (long long)resident * waves;
+        long long gx = need < per_graph ? need : per_graph;
+        return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+    };
+    dim3 gc = grid(res_cn[traj], (long long)p.cn_pos_lim * p.cns_pos << p.chunk_shift);
+    dim3 gv = grid(res_vn[traj], (long long)p.n << p.chunk_shift);
+    const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
+    cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
+    if (sample) cudaEventRecord(ev[0], st);
+    g_prof.launches += 2;
+    if (traj) bp_cn_wave_kernel<DC, true><<<gc, block, 0, st>>>(p);
+    else bp_cn_wave_kernel<DC, false><<<gc, block, 0, st>>>(p);
+    if (sample) cudaEventRecord(ev[1], st);
+    if (traj) bp_vn_wave_kernel<DV, true><<<gv, block, 0, st>>>(p);
+    else bp_vn_wave_kernel<DV, false><<<gv, block, 0, st>>>(p);
+    if (sample) {
+        cudaEventRecord(ev[2], st);
+        g_prof.iter_idx[g_prof.n_samples++] = p.iter;
+    }
+}
+
+int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves)
+{
+    if (dv == 4 && dc == 8) launch_wave_iteration<4, 8>(p, traj, st, waves);
+    else if (dv == 3 && dc == 6) launch_wave_iteration<3, 6>(p, traj, st, waves);
+    else if (dv == 5 && dc == 10) launch_wave_iteration<5, 10>(p, traj, st, waves);
+    else if (dv == 3 && dc == 9) launch_wave_iteration<3, 9>(p, traj, st, waves);
+    else if (dv == 4 && dc == 12) launch_wave_iteration<4, 12>(p, traj, st, waves);
+    else return -1;
+    return 0;
+}
+
+void bp_launch_wave_init(const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    bp_wave_init_kernel<<<p.G, 128, 0, st>>>(p);
+}
+
+}  // namespace scldpc

@@ -16,6 +16,8 @@ int bp_launch_iteration(int dv, int dc, const BpParams &p, bool traj, bool freez
 int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, cudaStream_t st);
 void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_frames, cudaStream_t st);
 void bp_launch_window_begin(const BpParams &p, int n_frames, cudaStream_t st);
+int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
+void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
 int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge, int32_t *scratch, int *err_dev, int G,
                        int n, int nk, int dv, int dc, cudaStream_t st);
 int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
@@ -124,6 +126,13 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.pos_cnt = c.take<int>(G * d->L * lanes);
     q.pos_pairs = c.take<int>(G * d->L * lanes);
     q.work = c.take<long long>(G * lanes);
+    q.y = c.take<u128>(G * n * ch);
+    q.pos_er_new = c.take<u64>(G * d->L * W);
+    q.vn_stamp = c.take<int>(G * d->L);
+    q.cn_list = c.take<int>(G * (d->L + d->dv - 1));
+    q.vn_list = c.take<int>(G * d->L);
+    q.n_list = c.take<int>(G * 2);
+    q.swept = c.take<long long>(G * 2);
     if (p) *p = q;
     return c.off;
 }
@@ -286,15 +295,31 @@ extern "C" int scldpc_channel_pack_host(const scldpc_dims_t *d, const uint8_t *e
 }
 
 // ---- decoders -------------------------------------------------------------------------------------------------
-// Runs up to `cap` flooding iterations over the ranges in *p, polling the device-side "graphs alive" counter every
-// `chunk` iterations (sweeps of a finished graph return at once, so overshoot costs launch latency only).
-static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool freeze, cudaStream_t st, int *launched)
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *s = getenv(name);
+    int v = s ? atoi(s) : dflt;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// Runs up to `cap` flooding iterations, in chunks.  The device keeps the number of graphs that still have an active
+// frame; after each chunk that counter is copied to pinned host memory and the NEXT chunk is enqueued before the
+// host waits for the copy, so the GPU never idles on the host.  Sweeps of a finished graph return at once, so the
+// overshoot (at most two chunks) costs launch latency only.
+static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool freeze, bool wave, cudaStream_t st, int *launched)
 {
     int *hf = nullptr, rc;
     if ((rc = host_flag(&hf))) return rc;
+    static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[0]) {
+        CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    }
     const int bps = blocks_per_sm_env();
-    const int chunk = 8;
-    int it = 0;
+    const int waves = env_int("SCLDPC_WAVES", 1, 1, 16);
+    const int chunk = env_int("SCLDPC_CHUNK", 8, 1, 64);
+    int it = 0, nchunk = 0;
+    bool pending[2] = {false, false};
     while (it < cap) {
         const int todo = (cap - it) < chunk ? (cap - it) : chunk;
         for (int q = 0; q < todo; q++, it++) {
@@ -302,13 +327,22 @@ static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool 
             p->max_it = cap;
             p->first_iter = (it == 0);
             p->row = traj ? it : -1;
-            if (bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+            if (wave ? bp_launch_wave_iteration(dv, dc, *p, traj, st, waves) : bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps))
+                return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
         CU(cudaGetLastError());
         if (it >= cap) break;
-        CU(cudaMemcpyAsync(hf, p->alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (*hf == 0) break;
+        const int slot = nchunk & 1;
+        CU(cudaMemcpyAsync(hf + slot, p->alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ev[slot], st));
+        pending[slot] = true;
+        nchunk++;
+        const int prev = nchunk & 1;            // the chunk before the one just enqueued
+        if (pending[prev]) {
+            CU(cudaEventSynchronize(ev[prev]));
+            pending[prev] = false;
+            if (hf[prev] == 0) break;
+        }
     }
     if (launched) *launched += it;
     return 0;
@@ -333,7 +367,11 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     p.stall_at_first = 1;
     p.win_edges = 2ll * p.E;
     int launched = 0;
-    if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, st, &launched))) return rc;
+    // wave tracking (bp_wave_kernels.cu) unless disabled or the chain is longer than its shared-memory bitmaps
+    const bool wave = d->L + d->dv - 1 <= 1024 && !env_int("SCLDPC_NO_WAVE", 0, 0, 1);
+    p.cn_pos_lim = term ? d->L + d->dv - 1 : d->L;
+    if (wave) bp_launch_wave_init(p, st);
+    if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, wave, st, &launched))) return rc;
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   (flags & SCLDPC_F_EXP_ALL) ? 1 : 0, 1, 0};
     if (d->n_frames == 0) CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
@@ -381,7 +419,7 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
         p.win_edges = ce + (v1 - v0) * d->dv;
         bp_launch_window_begin(p, d->n_frames, st);
         const int NumIt = (square && posW == 0) ? cap0 : cap;      // BP_SW.c:699-702
-        if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, st, nullptr))) return rc;
+        if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr))) return rc;
     }
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   1, square ? ms : 0, square ? W - 2 : W - 2 - ms};   // posW in [ms, W-2] (BP_SW.c:846-847)
@@ -399,6 +437,22 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
 }
 
 // ---- instrumentation --------------------------------------------------------------------------------------------
+// Positions swept by the last scldpc_bp_full call on this workspace, summed over graphs and iterations:
+// out[0] = CN positions, out[1] = VN positions (a sweep of everything would be iterations*(L+dv-1) and iterations*L).
+extern "C" int scldpc_bp_sweep_stats(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, long long *out_host)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!workspace_dev || !out_host) return fail(SCLDPC_EINVAL, "NULL pointer");
+    BpParams p;
+    carve(d, flags, workspace_dev, &p);
+    std::vector<long long> h(2 * (size_t)d->n_graphs);
+    CU(cudaMemcpy(h.data(), p.swept, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    out_host[0] = out_host[1] = 0;
+    for (int g = 0; g < d->n_graphs; g++) { out_host[0] += h[2 * g]; out_host[1] += h[2 * g + 1]; }
+    return 0;
+}
+
 extern "C" long long scldpc_launch_count(int reset)
 {
     long long v = g_prof.launches;

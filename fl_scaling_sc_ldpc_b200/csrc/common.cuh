@@ -56,6 +56,28 @@ __device__ __forceinline__ void sparse_count(int *cnt, int base, u128 m)
     while (a) { int b = __ffsll((long long)a) - 1; atomicAdd(&cnt[base + 64 + b], 1); a &= a - 1; }
 }
 
+// one adjacency row (dc CN edges / dv VN slots) with the widest aligned loads the degree allows
+template <int D>
+__device__ __forceinline__ void load_row(const int32_t *row, int (&e)[D])
+{
+    if constexpr (D % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < D / 4; q++) {
+            int4 t = __ldg(reinterpret_cast<const int4 *>(row) + q);
+            e[4 * q] = t.x; e[4 * q + 1] = t.y; e[4 * q + 2] = t.z; e[4 * q + 3] = t.w;
+        }
+    } else if constexpr (D % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < D / 2; q++) {
+            int2 t = __ldg(reinterpret_cast<const int2 *>(row) + q);
+            e[2 * q] = t.x; e[2 * q + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < D; q++) e[q] = __ldg(row + q);
+    }
+}
+
 // Internal parameter block (by value to every BP kernel).
 struct BpParams {
     // dimensions
@@ -82,6 +104,15 @@ struct BpParams {
     int *pos_cnt;             // [G][L][lanes] erased VNs per position (finalisation)
     int *pos_pairs;           // [G][L][lanes] accepted size-two stopping sets per position
     long long *work;          // [G][lanes] edge updates (window decoder)
+    // wave tracking (full BP): sweeps visit only positions whose inputs changed
+    u128 *y;                  // [G][n][chunks] "some outgoing Lji is an erasure" plane (with x: the VN's output state)
+    u64 *pos_er_new;          // [G][L][W] scratch of pos_er for the positions swept in this iteration
+    int *vn_stamp;            // [G][L] last iteration in which a VN of the position changed an outgoing message
+    int *cn_list;             // [G][L+dv-1] CN positions to sweep
+    int *vn_list;             // [G][L] VN positions to sweep
+    int *n_list;              // [G][2] lengths of cn_list / vn_list
+    int cn_pos_lim;           // CN positions that are ever swept (L+dv-1 terminated, L truncated)
+    long long *swept;         // [G][2] CN / VN positions swept, summed over iterations (instrumentation)
     // outputs
     int *iters;               // [G][lanes]
     int *rows;                // [G][max_rows][lanes][3]

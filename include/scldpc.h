@@ -135,11 +135,13 @@ int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const 
                        int32_t *erasures_p1_host, uint8_t *vn_erased_host, int32_t *rows_host, int max_rows);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
-/* kernels launched by the library since the last reset */
+/* kernels launched by the library since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
+ * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change) */
 long long scldpc_launch_count(int reset);
 /* Sampled CUDA-event timing of the two sweeps of every sample_every-th flooding iteration (on the launching
  * stream).  profile_end synchronises the device and returns per sample the iteration index and the CN / VN sweep
  * durations in milliseconds. */
+int scldpc_bp_sweep_stats(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, long long *out_host);
 int scldpc_profile_begin(int sample_every, int max_samples);
 int scldpc_profile_end(int *n_samples, int *iter_idx, float *cn_ms, float *vn_ms, int capacity);
 

@@ -33,8 +33,19 @@ def check_bp(res, ref, rows=False):
                 assert (res.rows[g, f, :k] == ref["rows"][g, f, :k]).all(), (g, f)
 
 
+@pytest.fixture(params=["wave", "sweep_all"])
+def sweep_mode(request, monkeypatch):
+    """full BP runs with wave tracking (only positions whose inputs changed are swept) and with every position swept
+    in every iteration, like the reference; both must be bit-identical to the oracle"""
+    if request.param == "sweep_all":
+        monkeypatch.setenv("SCLDPC_NO_WAVE", "1")
+    else:
+        monkeypatch.delenv("SCLDPC_NO_WAVE", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("dv,dc,L,M", [(4, 8, 10, 50), (3, 6, 10, 48), (5, 10, 12, 40), (4, 8, 6, 16), (4, 8, 20, 128)])
-def test_full_bp_matches_oracle(dv, dc, L, M):
+def test_full_bp_matches_oracle(dv, dc, L, M, sweep_mode):
     eps = [0.30, 0.42, 0.46, 0.50, 0.56] if dv != 3 else [0.3, 0.38, 0.42, 0.47]
     graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=70, eps_list=eps, seed=1000 + L + M, doped_every=9)
     fb = make_batch(dv, dc, L, M, graphs, chan)
@@ -45,6 +56,19 @@ def test_full_bp_matches_oracle(dv, dc, L, M):
             check_bp(res, ref)
             rest = eng.decode_bp_full(fb, cap, is_term, trajectory=True, max_rows=64)
             check_bp(rest, ref, rows=True)
+
+
+def test_full_bp_long_chain_wave_tracking():
+    """a long chain at small M: the decoding wave leaves most positions idle for most iterations"""
+    dv, dc, L, M = 4, 8, 60, 64
+    graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=130, eps_list=[0.40, 0.44, 0.47], seed=909)
+    fb = make_batch(dv, dc, L, M, graphs, chan)
+    for is_term in (True, False):
+        ref = util.oracle_bp(graphs, chan, 0, int(is_term), max_rows=400)
+        res = eng.decode_bp_full(fb, 0, is_term, trajectory=True, max_rows=400)
+        check_bp(res, ref, rows=True)
+        check_bp(eng.decode_bp_full(fb, 0, is_term), ref)
+        check_bp(eng.decode_bp_full(fb, 25, is_term), util.oracle_bp(graphs, chan, 25, int(is_term), max_rows=1))
 
 
 def test_full_bp_lane_words_and_ragged_frames():
