@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscldpc.so")
+LIB_PATH = os.environ.get("SCLDPC_LIB") or os.path.join(HERE, "libscldpc.so")   # SCLDPC_LIB: A/B builds when tuning
 CSRC = os.path.join(HERE, "csrc")
 
 # flags (include/scldpc.h)
@@ -24,6 +24,7 @@ EXPORTS = [
     "scldpc_last_error", "scldpc_version", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
     "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_decode_host",
+    "scldpc_peel_workspace_bytes", "scldpc_peel_trajectories", "scldpc_peel_variance_accumulate", "scldpc_philox_picks",
     "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end", "scldpc_bp_sweep_stats",
 ]
 
@@ -70,6 +71,8 @@ def lib() -> ctypes.CDLL:
         L.scldpc_bp_workspace_bytes.restype = ctypes.c_size_t
         L.scldpc_graph_generate_scratch_bytes.restype = ctypes.c_size_t
         L.scldpc_launch_count.restype = ctypes.c_longlong
+        L.scldpc_peel_workspace_bytes.restype = ctypes.c_size_t
+        L.scldpc_philox_picks.restype = None
         _lib = L
     return _lib
 

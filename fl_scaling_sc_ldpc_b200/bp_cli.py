@@ -1,0 +1,176 @@
+"""Drop-ins for the three reference executables (``simulators_sc_ldpc/bp_decoding/CMakeLists.txt:8-10``):
+
+    bp_lim_iter INDEX W NUM_DOPED MAX_IT [DOPED...]            full BP, iteration-limited      (BP_FULL.c main_terminated :2057)
+    sw_lim_iter INDEX W NUM_DOPED MAX_IT INIT_IT [DOPED...]    sliding window (square window)  (BP_SW.c :2072)
+    bp_traj     INDEX W NUM_DOPED MAX_IT IS_TERM [DOPED...]    full BP trajectories            (BP_TRAJ.c :2068)
+
+Same positional arguments, same output file names and row formats.  What the reference fixes at
+compile time (``#define Def_dv/Def_dc/Def_L/Def_M/Def_epsIni/Def_epsDelta/Def_NUM_POINTS/...``, BP_FULL.c:22-67) are
+run-time options here, defaulting to the reference's values.  The reference reads the doped positions starting at
+argv[4], i.e. overlapping MAX_IT (BP_FULL.c:2083-2091); ``--compat-argv`` reproduces that, the default reads them after
+the documented arguments.
+
+Frames are decoded in batches on the GPU and accounted in frame order, so the early stop (``frame_err >=
+numero_frame_err``, willIstop BP_FULL.c:440) ends a point at the same frame as the sequential reference would.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from . import engine
+
+DEFAULTS = {
+    "bp_lim_iter": dict(M=500, eps_ini=0.48, eps_delta=0.00125, points=26, min_frame_err=1000, max_frames=1000),
+    "sw_lim_iter": dict(M=500, eps_ini=0.475, eps_delta=0.00125, points=18, min_frame_err=1000, max_frames=1000),
+    "bp_traj": dict(M=2500, eps_ini=0.46, eps_delta=0.005, points=1, min_frame_err=500, max_frames=500),
+}
+HEADER = "p BER FER BLER BER_EXP FER_EXP BLER_EXP n L f users_err frame_err block_err users_err_exp frame_err_exp block_err_exp\n"
+
+
+def result_row(eps, n, L, f, c):
+    """``risultati`` row (BP_FULL.c:499-515)."""
+    return "%f %e %e %e %e %e %e %d %d %d %d %d %d %d %d %d\n" % (
+        eps, c["users_err"] / n / f, c["frame_err"] / f, c["block_err"] / L / f, c["users_err_exp"] / n / f,
+        c["frame_err_exp"] / f, c["block_err_exp"] / L / f, n, L, f, c["users_err"], c["frame_err"], c["block_err"],
+        c["users_err_exp"], c["frame_err_exp"], c["block_err_exp"])
+
+
+def account(counters, residual, blocks_err, erasures_exp, blocks_err_exp, erasures_p1=0):
+    """``plr_computation`` (BP_FULL.c:1503-1520) for one frame."""
+    if residual > 0:
+        counters["users_err"] += int(residual)
+        counters["frame_err"] += 1
+        counters["block_err"] += int(blocks_err)
+    if erasures_exp > 0:
+        counters["users_err_exp"] += int(erasures_exp)
+        counters["frame_err_exp"] += 1
+        counters["block_err_exp"] += int(blocks_err_exp)
+    if erasures_p1 > 0:
+        counters["frame_errP1"] += 1
+
+
+def new_counters():
+    return dict(users_err=0, frame_err=0, block_err=0, users_err_exp=0, frame_err_exp=0, block_err_exp=0, frame_errP1=0)
+
+
+def trajectory_text(rows: np.ndarray, iters: int) -> str:
+    """decodeBP's per-frame text (BP_TRAJ.c:988,1051,1145): ``iter\\tdeg1\\tdVNs\\tfirst_pos`` lines + a blank line."""
+    out = []
+    for t in range(iters):
+        out.append("%d\t%d\t%d\t%d\n" % (t, rows[t, 0], rows[t, 1], rows[t, 2]))
+    out.append("\n")
+    return "".join(out)
+
+
+def _parser(prog):
+    d = DEFAULTS[prog]
+    ap = argparse.ArgumentParser(prog=prog)
+    ap.add_argument("index", type=int)
+    ap.add_argument("W", type=int)
+    ap.add_argument("num_doped", type=int)
+    ap.add_argument("max_it", type=int)
+    if prog == "sw_lim_iter":
+        ap.add_argument("init_it", type=int)
+    if prog == "bp_traj":
+        ap.add_argument("is_term", type=int)
+    ap.add_argument("doped", type=int, nargs="*")
+    ap.add_argument("--dv", type=int, default=4)
+    ap.add_argument("--dc", type=int, default=8)
+    ap.add_argument("--L", type=int, default=50)
+    ap.add_argument("--M", type=int, default=d["M"], help="Def_M: CNs per position (VNs per position = Def_M*dc/dv)")
+    ap.add_argument("--eps-ini", type=float, default=d["eps_ini"])
+    ap.add_argument("--eps-delta", type=float, default=d["eps_delta"])
+    ap.add_argument("--points", type=int, default=d["points"])
+    ap.add_argument("--min-frame-err", type=int, default=d["min_frame_err"])
+    ap.add_argument("--max-frames", type=int, default=d["max_frames"])
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--frames-per-graph", type=int, default=128)
+    ap.add_argument("--graphs-per-batch", type=int, default=4)
+    ap.add_argument("--compat-argv", action="store_true", help="read doped positions from argv[4] on like the reference")
+    ap.add_argument("--outdir", default=".")
+    return ap
+
+
+def run(prog: str, argv=None) -> int:
+    import os
+    import time
+    a = _parser(prog).parse_args(argv)
+    raw = list(sys.argv[1:] if argv is None else argv)
+    if a.compat_argv:
+        pos = [x for x in raw if not x.startswith("--")]
+        doped = [int(x) for x in pos[3:3 + a.num_doped]]              # argv[4..] of the C program
+    else:
+        doped = list(a.doped)[: a.num_doped]
+    seed = a.seed if a.seed is not None else int(time.time() * 1e6) & 0x7FFFFFFF     # srandom(tv_usec), BP_FULL.c:2059-2062
+    vns_pos = a.M * a.dc // a.dv
+    ens = engine.Ensemble(a.dv, a.dc, a.L, vns_pos)
+    max_it = max(1, a.max_it)                                          # do { } while (iter < MaxNumIt) runs at least once
+    init_it = getattr(a, "init_it", 0) or a.max_it                     # BP_SW.c:2099-2102
+    fpg, G = a.frames_per_graph, a.graphs_per_batch
+    nw = engine.words_for(fpg)
+    if prog == "sw_lim_iter":
+        name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_%dinit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, init_it, a.index)
+    else:
+        name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, a.index)
+    graph_id = 0
+    for sim in range(a.points):
+        eps = a.eps_ini - sim * a.eps_delta                            # inizio_sim, BP_FULL.c:300
+        c = new_counters()
+        f = 0
+        traj_f = None
+        if prog == "bp_traj":
+            tname = "trajectories_%.4f_%s_SC_LDPC_%d_%d_L%d_M%d_BP_Full_%dit_Random_BLER_%d.dat" % (
+                eps, "terminated" if a.is_term else "truncated", a.dv, a.dc, a.L, a.M, a.max_it, a.index)
+            traj_f = open(os.path.join(a.outdir, tname), "w")
+        stop = False
+        while f < a.max_frames and not stop:
+            fb = engine.FrameBatch(ens, G, fpg, nw)
+            fb.generate_graphs(seed, first_graph_id=graph_id)
+            fb.generate_erasures(eps, seed + 1, first_graph_id=graph_id, doping_points=doped)
+            graph_id += G
+            if prog == "sw_lim_iter":
+                r = engine.decode_bp_window(fb, a.W, max_it, max(1, init_it), square=True, is_term=True)
+            elif prog == "bp_traj":
+                r = engine.decode_bp_full(fb, max_it, is_term=bool(a.is_term), trajectory=True, max_rows=max_it)
+            else:
+                r = engine.decode_bp_full(fb, max_it, is_term=True)
+            for g in range(G):
+                for k in range(fpg):
+                    if f >= a.max_frames or stop:
+                        break
+                    if traj_f is not None:
+                        traj_f.write(trajectory_text(r.rows[g, k], int(r.iters[g, k])))
+                    account(c, r.residual[g, k], r.blocks_err[g, k], r.erasures_exp[g, k], r.blocks_err_exp[g, k],
+                            r.erasures_p1[g, k] if prog == "sw_lim_iter" else 0)
+                    f += 1
+                    if c["frame_err"] >= a.min_frame_err:              # willIstop, BP_FULL.c:440-451
+                        stop = True
+        if traj_f is not None:
+            traj_f.close()
+        with open(os.path.join(a.outdir, name), "w" if sim == 0 else "a") as out:
+            if sim == 0:
+                out.write(HEADER)
+            out.write(result_row(eps, ens.n, a.L, f, c))
+    return 0
+
+
+def bp_lim_iter(argv=None):
+    return run("bp_lim_iter", argv)
+
+
+def sw_lim_iter(argv=None):
+    return run("sw_lim_iter", argv)
+
+
+def bp_traj(argv=None):
+    return run("bp_traj", argv)
+
+
+if __name__ == "__main__":
+    prog = sys.argv[1] if len(sys.argv) > 1 else ""
+    if prog not in DEFAULTS:
+        sys.exit("usage: python -m fl_scaling_sc_ldpc_b200.bp_cli {bp_lim_iter|sw_lim_iter|bp_traj} ARGS...")
+    sys.exit(run(prog, sys.argv[2:]))

@@ -44,7 +44,7 @@ __global__ void bp_wave_init_kernel(BpParams p)
 // check-node sweep over the listed positions
 // ------------------------------------------------------------------------------------------------------------
 template <int DC, bool TRAJ>
-__global__ void __launch_bounds__(256) bp_cn_wave_kernel(BpParams p)
+__global__ void __launch_bounds__(256, TRAJ ? 3 : 5) bp_cn_wave_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
@@ -191,7 +191,7 @@ __device__ void bp_wave_retire(const BpParams &p, int g)
 // variable-node sweep over the listed positions
 // ------------------------------------------------------------------------------------------------------------
 template <int DV, bool TRAJ>
-__global__ void __launch_bounds__(256) bp_vn_wave_kernel(BpParams p)
+__global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(256) bp_vn_wave_kernel(BpParams p)
     const int ipp = p.vns_pos << p.chunk_shift;
     const int items = ld_cg(p.n_list + 2 * g + 1) * ipp;
     const int stride = gridDim.x * blockDim.x;
-    // the trip count is warp-uniform (the shuffle below needs the whole warp): bound by the warp's first item
+    // The trip count is warp-uniform because the row-write decision below is a shuffle over the ch adjacent threads
+    // that hold one VN.
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
         const int idx = base + (threadIdx.x & 31);
         const bool work = lane_work && idx < items;
@@ -235,11 +236,12 @@ __global__ void __launch_bounds__(256) bp_vn_wave_kernel(BpParams p)
             u128 in[DV];
 #pragma unroll
             for (int i = 0; i < DV; i++) in[i] = ld_stream(c2v + (size_t)s[i] * ch + k);
-            const u128 cv = ld_stream(chan + (size_t)v * ch + k);
-            u128 xdet;
-            if (p.first_iter) { xo = ones128(); xdet = cv; yo = cv; }      // Lji starts at the channel value
-            else { xo = x[(size_t)v * ch + k]; xdet = xo; yo = y[(size_t)v * ch + k]; }
-            u128 acc = cv;
+            // After the first iteration the channel value is implied by y: y = 1 needs chan = 1, and a frame with
+            // y = 0 has all-zero outgoing messages for good (incoming messages only go 1 -> 0), so chan is not read.
+            if (p.first_iter) { yo = ld_stream(chan + (size_t)v * ch + k); xo = ones128(); }
+            else { xo = x[(size_t)v * ch + k]; yo = y[(size_t)v * ch + k]; }
+            const u128 xdet = p.first_iter ? yo : xo;                      // Lji starts at the channel value
+            u128 acc = yo;
 #pragma unroll
             for (int i = 0; i < DV; i++) { out[i] = acc; acc &= in[i]; }
             xn = acc;

@@ -27,6 +27,11 @@ void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos,
                       uint64_t seed, uint64_t first_graph, cudaStream_t st);
 void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
 void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
+void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
+int peel_grid(int total_size, long long total_frames);
+int peel_launch(PeelParams p, int grid, cudaStream_t st);
+void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
+                          long long *counts, cudaStream_t st);
 }  // namespace scldpc
 
 using namespace scldpc;
@@ -433,6 +438,60 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
         for (long long x : w) tot += x;
         *edge_updates_host = tot;
     }
+    return 0;
+}
+
+// ---- peeling decoder ------------------------------------------------------------------------------------------------
+extern "C" void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uint32_t *out_host)
+{
+    if (out_host && n > 0) peel_picks_host(seed, frame_id, n, out_host);
+}
+
+extern "C" size_t scldpc_peel_workspace_bytes(const scldpc_dims_t *d, int n_cn_all, int total_size)
+{
+    if (check_dims(d) || have_device()) return 0;
+    const int grid = peel_grid(total_size, (long long)d->n_graphs * d->n_frames);
+    if (grid < 0) { fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap"); return 0; }
+    return sizeof(u64) * (size_t)grid * (size_t)n_cn_all;
+}
+
+extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *vn_cn_dev, const uint64_t *chan_dev, int n_cn_all,
+                                        int total_size, int num_steps, uint64_t seed, uint64_t first_frame_id, int32_t *r1_dev,
+                                        int32_t *recovered_dev, int32_t *n_erased_dev, void *workspace_dev, size_t workspace_bytes,
+                                        void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!vn_cn_dev || !chan_dev || !recovered_dev || !n_erased_dev || !workspace_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if (total_size < 1 || total_size > n_cn_all || num_steps < 0) return fail(SCLDPC_EINVAL, "bad total_size / num_steps");
+    if ((rc = have_device())) return rc;
+    const long long frames = (long long)d->n_graphs * d->n_frames;
+    if (frames == 0) return 0;
+    const int grid = peel_grid(total_size, frames);
+    if (grid < 0) return fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap");
+    if (workspace_bytes < sizeof(u64) * (size_t)grid * (size_t)n_cn_all) return fail(SCLDPC_ENOMEM, "workspace too small");
+    PeelParams p;
+    memset(&p, 0, sizeof p);
+    p.n = d->L * d->vns_pos; p.dv = d->dv; p.n_cn_all = n_cn_all; p.total_size = total_size; p.num_steps = num_steps;
+    p.W = d->n_words; p.n_frames = d->n_frames; p.G = d->n_graphs;
+    p.vn_cn = vn_cn_dev; p.chan = reinterpret_cast<const u64 *>(chan_dev); p.state = static_cast<u64 *>(workspace_dev);
+    p.r1 = r1_dev; p.recovered = recovered_dev; p.n_erased = n_erased_dev; p.seed = seed; p.first_frame = first_frame_id;
+    if (peel_launch(p, grid, static_cast<cudaStream_t>(stream))) return fail(SCLDPC_EINVAL, "peeling launch configuration failed");
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scldpc_peel_variance_accumulate(const int32_t *r1_dev, int n_frames, int row_len, const double *theory_dev, int S,
+                                               double M, double *ssq_dev, int64_t *counts_dev, void *stream)
+{
+    if (!r1_dev || !theory_dev || !ssq_dev || !counts_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if (S < 0 || S > row_len || n_frames < 0) return fail(SCLDPC_EINVAL, "bad sizes");
+    int rc = have_device();
+    if (rc) return rc;
+    if (S == 0) return 0;
+    peel_variance_launch(r1_dev, n_frames, row_len, theory_dev, S, M, ssq_dev, reinterpret_cast<long long *>(counts_dev),
+                         static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
     return 0;
 }
 

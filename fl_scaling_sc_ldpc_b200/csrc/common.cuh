@@ -134,6 +134,19 @@ struct BpFinalOut {
     int p1_lo, p1_hi;    // positions whose erasures count towards NumErasuresP1 (BP_SW.c:846-847); empty if lo > hi
 };
 
+// Parameter block of the peeling kernel (peel_kernels.cu).
+struct PeelParams {
+    int n, dv, n_cn_all, total_size, num_steps, W, n_frames, G;
+    int n_words1, n_l1, n_l2;      // bitmap words, level-1 entries (1024 CNs each), level-2 entries (32768 CNs each)
+    const int32_t *vn_cn;          // [G][n][dv]
+    const u64 *chan;               // [G][n][W]
+    u64 *state;                    // [gridDim.x][n_cn_all]  (degree << 32) + id sum
+    int32_t *r1;                   // [G][n_frames][num_steps+1] or NULL
+    int32_t *recovered;            // [G][n_frames]
+    int32_t *n_erased;             // [G][n_frames]
+    uint64_t seed, first_frame;
+};
+
 namespace scldpc {
 // host-side instrumentation shared by the launchers (capi.cu owns the storage)
 struct Profiler {

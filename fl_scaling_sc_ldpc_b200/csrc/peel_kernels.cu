@@ -1,2 +1,242 @@
-// peel_kernels.cu -- placeholder translation unit, filled in by the peeling decoder (K3).
+// peel_kernels.cu -- random-order peeling decoder with the per-step degree-one-CN trajectory (sm_100a).
+//
+// Replaces the hot loop of simulate_peeling_decoder_ldpc (PD.py:705-789): at every step pick, uniformly at random, one
+// of the check nodes of residual degree one "in ascending CN order" (pick_random_deg_1_cn, PD.py:1022-1026:
+// np.flatnonzero(r == 1) + random.choice), remove its variable node from the residual graph, and record how many
+// degree-one CNs are left.  The reference pays O(#CN) twice per step (flatnonzero, count_nonzero); here
+//   * one warp owns one frame; frames are independent, so thousands run concurrently and hide each other's latency;
+//   * the degree-one set is a bitmap in shared memory under a 3-level popcount hierarchy (32 x 32 x 32 fan-out),
+//     so "the k-th degree-one CN in ascending order" is three warp-wide prefix sums + one __fns;
+//   * CN state lives in global memory as one 64-bit word per CN: (residual degree << 32) + (sum of the ids of the
+//     erased VNs still attached).  A CN of degree one therefore names its VN directly (head(schedule[m]), PD.py:769),
+//     and removing a VN is one 64-bit atomicAdd per edge whose return value says whether the CN became / stopped
+//     being degree one.
+// The random pick of step s of frame f is k = philox4x32_10(counter = (s/4, 0, f.lo, f.hi), key = seed)[s%4] mod
+// (number of degree-one CNs); the oracle is fed the same 32-bit draws, so trajectories are compared bit for bit.
 #include "common.cuh"
+
+namespace scldpc {
+
+__host__ __device__ __forceinline__ void philox_peel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                     uint32_t k1, uint32_t (&out)[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// host helper (tests / reproducibility): the 32-bit draws of one frame
+void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out)
+{
+    for (int s = 0; s < n; s += 4) {
+        uint32_t r[4];
+        philox_peel((uint32_t)(s >> 2), 0u, (uint32_t)frame_id, (uint32_t)(frame_id >> 32), (uint32_t)seed ^ 0x7065656Cu,
+                    (uint32_t)(seed >> 32), r);
+        for (int h = 0; h < 4 && s + h < n; h++) out[s + h] = r[h];
+    }
+}
+
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// one warp per block; dynamic shared memory: bitmap words | level-1 counts | level-2 counts
+__global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
+{
+    extern __shared__ unsigned s_mem[];
+    unsigned *bits = s_mem;
+    int *l1 = reinterpret_cast<int *>(s_mem + p.n_words1);
+    int *l2 = l1 + p.n_l1;
+    const int lane = threadIdx.x;
+    u64 *st = p.state + (size_t)blockIdx.x * p.n_cn_all;
+    const long long total_frames = (long long)p.G * p.n_frames;
+
+    for (long long fr = blockIdx.x; fr < total_frames; fr += gridDim.x) {
+        const int g = (int)(fr / p.n_frames), f = (int)(fr % p.n_frames);
+        const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * p.dv;
+        const u64 *chan = p.chan + (size_t)g * p.n * p.W + (f >> 6);
+        const int fb = f & 63;
+        // ---- residual graph of the erased VNs (schedule, PD.py:750-757) ----
+        for (int i = lane; i < p.n_cn_all; i += 32) st[i] = 0;
+        for (int i = lane; i < p.n_words1 + p.n_l1 + p.n_l2; i += 32) s_mem[i] = 0;
+        __syncwarp();
+        int n_er = 0;
+        for (int v0 = 0; v0 < p.n; v0 += 32) {
+            const int v = v0 + lane;
+            if (v < p.n && ((chan[(size_t)v * p.W] >> fb) & 1ull)) {
+                n_er++;
+                for (int i = 0; i < p.dv; i++)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(st + vn_cn[(size_t)v * p.dv + i]), (1ull << 32) + (u64)v);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) n_er += __shfl_xor_sync(0xffffffffu, n_er, o);
+        __threadfence_block();
+        __syncwarp();
+        // ---- degree-one bitmap over the CNs the decoder sees (t < total_size, PD.py:756-758) ----
+        int cnt1 = 0;
+        for (int w = 0; w < p.n_words1; w++) {
+            const int c = w * 32 + lane;
+            const bool one = c < p.total_size && (__ldcg(reinterpret_cast<const unsigned long long *>(st + c)) >> 32) == 1ull;
+            const unsigned m = __ballot_sync(0xffffffffu, one);
+            if (lane == 0 && m) {
+                bits[w] = m;
+                const int pc = __popc(m);
+                l1[w >> 5] += pc;
+                l2[w >> 10] += pc;
+            }
+            cnt1 += __popc(m);
+        }
+        __syncwarp();
+        int32_t *r1 = p.r1 ? p.r1 + (size_t)fr * (p.num_steps + 1) : nullptr;
+        if (r1 && lane == 0) r1[0] = cnt1;
+        const uint64_t fid = p.first_frame + (uint64_t)fr;
+        int recovered = 0;
+        uint32_t rnd[4] = {0, 0, 0, 0};
+        int step = 0;
+        for (; step < p.num_steps; step++) {
+            if (cnt1 == 0) break;                               // stalled or finished: r1 stays put (PD.py:765-767)
+            if ((step & 3) == 0)
+                philox_peel((uint32_t)(step >> 2), 0u, (uint32_t)fid, (uint32_t)(fid >> 32), (uint32_t)p.seed ^ 0x7065656Cu,
+                            (uint32_t)(p.seed >> 32), rnd);
+            int k = (int)(rnd[step & 3] % (uint32_t)cnt1);
+            // ---- select the k-th set bit ----
+            int a = lane < p.n_l2 ? l2[lane] : 0;
+            int inc = warp_incl_scan(a, lane);
+            unsigned bal = __ballot_sync(0xffffffffu, k < inc);
+            int sel = __ffs(bal) - 1;
+            k -= __shfl_sync(0xffffffffu, inc - a, sel);
+            const int b2 = sel;
+            a = (b2 * 32 + lane) < p.n_l1 ? l1[b2 * 32 + lane] : 0;
+            inc = warp_incl_scan(a, lane);
+            bal = __ballot_sync(0xffffffffu, k < inc);
+            sel = __ffs(bal) - 1;
+            k -= __shfl_sync(0xffffffffu, inc - a, sel);
+            const int b1 = b2 * 32 + sel;
+            const int wi = b1 * 32 + lane;
+            const unsigned word = wi < p.n_words1 ? bits[wi] : 0u;
+            a = __popc(word);
+            inc = warp_incl_scan(a, lane);
+            bal = __ballot_sync(0xffffffffu, k < inc);
+            sel = __ffs(bal) - 1;
+            k -= __shfl_sync(0xffffffffu, inc - a, sel);
+            const unsigned wsel = __shfl_sync(0xffffffffu, word, sel);
+            const int m = (b1 * 32 + sel) * 32 + (int)__fns(wsel, 0, k + 1);
+            // ---- remove its VN (PD.py:769-780) ----
+            const int v = (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long *>(st + m));
+            recovered++;
+            int delta = 0;
+            if (lane < p.dv) {
+                const int c = vn_cn[(size_t)v * p.dv + lane];
+                const u64 old = atomicAdd(reinterpret_cast<unsigned long long *>(st + c), ~((1ull << 32) + (u64)v) + 1ull);
+                const int deg_old = (int)(old >> 32);
+                if (c < p.total_size) {                          // CNs >= total_size are not seen by the decoder
+                    if (deg_old == 2) {                          // becomes degree one
+                        atomicOr(&bits[c >> 5], 1u << (c & 31));
+                        atomicAdd(&l1[c >> 10], 1);
+                        atomicAdd(&l2[c >> 15], 1);
+                        delta = 1;
+                    } else if (deg_old == 1) {                   // stops being degree one
+                        atomicAnd(&bits[c >> 5], ~(1u << (c & 31)));
+                        atomicSub(&l1[c >> 10], 1);
+                        atomicSub(&l2[c >> 15], 1);
+                        delta = -1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+            cnt1 += delta;
+            __syncwarp();
+            if (r1 && lane == 0) r1[step + 1] = cnt1;             // PD.py:781
+        }
+        if (r1)
+            for (int s = step + 1 + lane; s <= p.num_steps; s += 32) r1[s] = cnt1;   // copies of the last value
+        if (lane == 0) {
+            p.recovered[fr] = recovered;
+            p.n_erased[fr] = n_er;
+        }
+        __syncwarp();
+    }
+}
+
+// calc_var_chunk (EST.py:131-138) on the device: for step s, over the frames in order,
+//   ssq[s] += (r1/M - theory[s]/M)^2 for frames with r1 != 0,   counts[s] += (r1 != 0)
+// Sums run over frames sequentially in double precision without FMA contraction, the order np.nansum(axis=0) uses.
+__global__ void peel_variance_kernel(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M,
+                                     double *ssq, long long *counts)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const double th = __ddiv_rn(theory[s], M);
+    double acc = 0.0;
+    long long cnt = 0;
+    for (int f = 0; f < n_frames; f++) {
+        const int v = r1[(size_t)f * row_len + s];
+        if (v != 0) {
+            const double c = __dsub_rn(__ddiv_rn((double)v, M), th);
+            acc = __dadd_rn(acc, __dmul_rn(c, c));
+            cnt++;
+        }
+    }
+    ssq[s] = __dadd_rn(ssq[s], acc);
+    counts[s] += cnt;
+}
+
+size_t peel_smem_bytes(int total_size, int *n_words1, int *n_l1, int *n_l2)
+{
+    const int w = (total_size + 31) / 32, a = (w + 31) / 32, b = (a + 31) / 32;
+    if (n_words1) *n_words1 = w;
+    if (n_l1) *n_l1 = a;
+    if (n_l2) *n_l2 = b;
+    return sizeof(unsigned) * ((size_t)w + a + b);
+}
+
+int peel_grid(int total_size, long long total_frames)
+{
+    int dev = 0, sms = 148, max_smem = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t smem = peel_smem_bytes(total_size, nullptr, nullptr, nullptr);
+    if (smem > (size_t)max_smem) return -1;
+    long long per_sm = (long long)(max_smem) / (long long)(smem + 1024);
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = per_sm * sms;
+    if (grid > total_frames) grid = total_frames;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+int peel_launch(PeelParams p, int grid, cudaStream_t st)
+{
+    const size_t smem = peel_smem_bytes(p.total_size, &p.n_words1, &p.n_l1, &p.n_l2);
+    if (p.n_l2 > 32) return -1;                                  // more than 2^20 CNs: one more level would be needed
+    if (cudaFuncSetAttribute(peel_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    g_prof.launches += 1;
+    peel_trajectory_kernel<<<grid, 32, smem, st>>>(p);
+    return 0;
+}
+
+void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
+                          long long *counts, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    peel_variance_kernel<<<(S + 255) / 256, 256, 0, st>>>(r1, n_frames, row_len, theory, S, M, ssq, counts);
+}
+
+}  // namespace scldpc

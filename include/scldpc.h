@@ -134,6 +134,29 @@ int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const 
                        int32_t *blocks_err_host, int32_t *erasures_exp_host, int32_t *blocks_err_exp_host,
                        int32_t *erasures_p1_host, uint8_t *vn_erased_host, int32_t *rows_host, int max_rows);
 
+/* ---- peeling decoder with degree-one trajectory -------------------------------------------------------------- */
+/* simulate_peeling_decoder_ldpc's per-frame loop (PD.py:740-785) for d->n_graphs graphs x d->n_frames frames:
+ *   vn_cn_dev  [G][n][dv]  `transmissions` (SC.gen_slots, SC.py:53); CN indices run over n_cn_all CNs
+ *   chan_dev   [G][n][W]   erased VNs, i.e. the Users that are generated (PD.py:154-163, :174-195 after doping)
+ *   total_size             CNs the decoder sees: cns_per_pos * num_positions (PD.py:717-719); the rest are ignored
+ *   num_steps              num_pd_steps = int(M * num_positions * (e + 0.1)) -- evaluate it in Python (PD.py:721)
+ * Step s of global frame F = first_frame_id + g*n_frames + f picks the (u mod k)-th degree-one CN in ascending order,
+ * u = scldpc_philox_picks(seed, F)[s], k = number of degree-one CNs (pick_random_deg_1_cn, PD.py:1022-1026).
+ * Outputs: r1_dev int32 [G][n_frames][num_steps+1] (may be NULL), recovered_dev / n_erased_dev int32 [G][n_frames]
+ * (plrs = (n_erased - recovered) / total_generated, PD.py:785). */
+size_t scldpc_peel_workspace_bytes(const scldpc_dims_t *d, int n_cn_all, int total_size);
+int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *vn_cn_dev, const uint64_t *chan_dev, int n_cn_all,
+                             int total_size, int num_steps, uint64_t seed, uint64_t first_frame_id, int32_t *r1_dev,
+                             int32_t *recovered_dev, int32_t *n_erased_dev, void *workspace_dev, size_t workspace_bytes,
+                             void *stream);
+/* calc_var_chunk (fl_scaling/est_scaling_params.py:131-138) fused on the device: for s < S, over the frames in order,
+ * ssq[s] += (r1/M - theory[s]/M)^2 and counts[s] += 1 for frames with r1 != 0 (float64, same summation order as
+ * np.nansum(axis=0)).  r1_dev has row_len columns. */
+int scldpc_peel_variance_accumulate(const int32_t *r1_dev, int n_frames, int row_len, const double *theory_dev, int S,
+                                    double M, double *ssq_dev, int64_t *counts_dev, void *stream);
+/* the 32-bit draws behind the picks of one frame (host function; used to feed the reference the same pick sequence) */
+void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uint32_t *out_host);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* kernels launched by the library since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
  * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change) */

@@ -1,0 +1,165 @@
+"""GPU parity tests of the peeling path (peel_kernels.cu, peeling_decoding.py) against the reference's own outputs
+(tests/golden/peel_golden.npz) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fl_scaling_sc_ldpc_b200 as eng
+import oracle
+from fl_scaling_sc_ldpc_b200 import peeling_decoding as pdx
+
+pytestmark = pytest.mark.gpu
+Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "peel_golden.npz"))
+PEEL_SEED = 777
+
+
+def _params(name):
+    e, l, r, L, M, term = Z[name + "_params"]
+    return float(e), int(l), int(r), int(L), int(M), bool(term)
+
+
+@pytest.mark.parametrize("name", ["t0", "t1", "t2", "t3"])
+def test_peel_trajectories_match_reference(name):
+    """r1 of the CUDA kernel == r1 of the reference's simulate_peeling_decoder_ldpc, same code / erasures / picks"""
+    e, l, r, L, M, term = _params(name)
+    cns, num_positions, total_size, steps = pdx._peel_geometry(e, l, r, L, M, term)
+    F = Z[name + "_tr"].shape[0]
+    ens = eng.Ensemble(l, r, L, M)
+    # one frame per graph (the reference draws a new code per frame): G = F graphs x 1 frame
+    fb = eng.FrameBatch(ens, F, 1, 2).set_graphs(Z[name + "_tr"])
+    er = np.unpackbits(Z[name + "_er"], axis=1)[:, : L * M]
+    fb.set_erasures(er[:, None, :])
+    r1, rec, ner = pdx.peel_batch(ens, fb, total_size, steps, PEEL_SEED, 0)
+    assert (r1.reshape(F, -1).cpu().numpy() == Z[name + "_r1"]).all()
+    total_generated = (L - len(Z[name + "_doping"])) * M
+    plrs = (ner - rec).reshape(-1).cpu().numpy() / total_generated
+    assert np.allclose(plrs, Z[name + "_plrs"], rtol=0, atol=1e-15)
+
+
+def test_peel_many_frames_per_graph_matches_oracle():
+    """frames sharing a code, ragged frame count, terminated and non-terminated, picks from the frame's Philox stream"""
+    l, r, L, M, e = 4, 8, 16, 64, 0.45
+    ens = eng.Ensemble(l, r, L, M)
+    G, F = 3, 37
+    fb = eng.FrameBatch(ens, G, F, 2).generate_graphs(5).generate_erasures(e, 6)
+    vn_cn = fb.vn_cn.cpu().numpy()
+    er = fb.erasures_host()
+    for term in (False, True):
+        cns, num_positions, total_size, steps = pdx._peel_geometry(e, l, r, L, M, term)
+        r1, rec, ner = pdx.peel_batch(ens, fb, total_size, steps, 99, 1000)
+        r1 = r1.cpu().numpy(); rec = rec.cpu().numpy(); ner = ner.cpu().numpy()
+        for g in range(G):
+            for f in range(0, F, 5):
+                picks = pdx.philox_picks(99, 1000 + g * F + f, steps)
+                o_r1, o_rec = oracle.peel_trajectory(vn_cn[g], er[g, f], total_size, ens.nk, steps, picks)
+                assert (r1[g, f] == o_r1).all(), (term, g, f)
+                assert rec[g, f] == o_rec and ner[g, f] == er[g, f].sum()
+
+
+def test_variance_accumulation_matches_numpy():
+    """calc_nu_chunk / calc_var_chunk (est_scaling_params.py:90-94,131-138) restated in NumPy vs the fused kernel"""
+    rng = np.random.default_rng(3)
+    F, S = 23, 700
+    r1 = rng.integers(0, 40, size=(F, S + 11)).astype(np.int32)
+    r1[:, 500:] *= (rng.random((F, S + 11 - 500)) < 0.5)
+    theory = np.concatenate([rng.random(S) * 30 + 0.1, np.zeros(5)])
+    M = 1000
+    # NumPy restatement of the reference functions
+    crop = r1[:, : np.max(np.where(theory > 0)) + 1][:, 0:theory.shape[0]].astype(np.int64)
+    th = theory[theory > 0] / M
+    r1s = crop / M
+    cen = r1s - th
+    cen[r1s == 0] = np.nan
+    ssq_ref = np.nansum(cen ** 2, axis=0)
+    cnt_ref = np.sum(~np.isnan(cen), axis=0)
+    chunks = [torch.as_tensor(r1[:10]).cuda(), torch.as_tensor(r1[10:]).cuda()]
+    ssq, cnt = pdx.calc_nu_chunk_device(chunks, theory, M)
+    assert (cnt == cnt_ref).all()
+    # two chunks are summed chunk-wise like main_simulate_variance does; compare with the same association
+    def chunk(a):
+        c = a[:, :S] / M - th
+        c[a[:, :S] == 0] = np.nan
+        return np.nansum(c ** 2, axis=0)
+    assert np.array_equal(ssq, chunk(r1[:10].astype(np.int64)) + chunk(r1[10:].astype(np.int64)))
+    assert np.allclose(ssq, ssq_ref, rtol=1e-13)
+
+
+def test_simulate_peeling_decoder_ldpc_signature_and_shapes():
+    _, r1, plrs = pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, False, 6, seed=1)
+    assert r1.shape == (6, int(40 * 12 * (0.46 + 0.1)) + 1) and r1.dtype == np.dtype("int") and plrs.shape == (6,)
+    assert (r1[:, 0] > 0).all() and (plrs >= 0).all() and (plrs <= 1).all()
+    _, r1b, plrsb = pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, False, 6, seed=1)
+    assert (r1 == r1b).all() and (plrs == plrsb).all()                      # reproducible
+    _, r1c, _ = pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, False, 6, [5, 6], seed=1)
+    assert r1c.shape == r1.shape
+    with pytest.raises(NotImplementedError):
+        pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, True, 2)
+
+
+@pytest.mark.parametrize("name", ["s0", "s1", "s2"])
+def test_simulate_sc_ldpc_matches_reference(name):
+    """the 13-tuple of the reference's simulate_sc_ldpc on the same injected codes and erasure masks"""
+    e, l, r, L, M, term = _params(name)
+    tail = 0 if term else 20
+    Leff = L + tail
+    tr_all = Z[name + "_tr"]
+    er_all = np.unpackbits(Z[name + "_er"], axis=1)[:, : Leff * M]
+    F = tr_all.shape[0]
+
+    def factory(ens, G, fpg, gid0):
+        assert fpg == 1
+        fb = eng.FrameBatch(ens, G, 1, 2).set_graphs(tr_all[gid0:gid0 + G])
+        return fb.set_erasures(er_all[gid0:gid0 + G, None, :])
+
+    out = pdx.simulate_sc_ldpc(e, l, r, L, M, term, False, True, False, F, 10 ** 9, [], frames_per_graph=1, graphs_per_batch=5,
+                               progress=False, _batch_factory=factory)
+    got = [out[i] for i in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12)]
+    assert np.allclose(got, Z[name + "_out"], rtol=0, atol=1e-15), (got, list(Z[name + "_out"]))
+    assert out[8].shape == (F,) and not out[8].any() and not out[9].any()
+
+
+def test_simulate_sc_ldpc_early_stop_is_sequential():
+    """max_fuckups cuts at the same frame no matter how frames are batched (PD.py:698)"""
+    a = pdx.simulate_sc_ldpc(0.52, 4, 8, 10, 32, True, False, True, False, 400, 7, [], seed=3, frames_per_graph=128,
+                             graphs_per_batch=1, progress=False)
+    b = pdx.simulate_sc_ldpc(0.52, 4, 8, 10, 32, True, False, True, False, 400, 7, [], seed=3, frames_per_graph=128,
+                             graphs_per_batch=3, progress=False)
+    assert a[5] == b[5] and a[:8] == b[:8] and a[4] <= 7 and round(a[0] * a[5]) == 7
+
+
+def test_generated_ensemble_is_valid_and_uniformish():
+    """on-device generate_code / gen_slots: every CN position receives a permutation of its sockets"""
+    from fl_scaling_sc_ldpc_b200 import sc_ldpc as scx
+    l, r, L, M = 4, 8, 9, 48
+    cns = M * l // r
+    scx.set_seed(11)
+    tr = scx.gen_slots(l, r, L, M)
+    assert tr.shape == (L * M, l) and tr.dtype == np.int64
+    pos = np.repeat(np.arange(L), M)
+    for d in range(l):
+        assert ((tr[:, d] // cns) == pos + d).all()                        # edge d goes to CN position i + d
+    deg = np.bincount(tr.reshape(-1), minlength=(L + l - 1) * cns)
+    assert (deg[(l - 1) * cns: L * cns] == r).all() and deg.max() <= r      # interior CNs have degree r
+    tb = scx.gen_slots_tail_biting(l, r, L, M)
+    assert (np.bincount(tb.reshape(-1), minlength=L * cns) == r).all() and tb.max() < L * cns
+    # different graph ids give different codes; the socket of VN 0 / edge 0 is roughly uniform over the CNs
+    firsts = np.array([scx.gen_slots(l, r, L, M)[0, 0] for _ in range(200)])
+    assert len(set(firsts.tolist())) > 15 and firsts.max() < cns
+
+
+def test_generated_channel_statistics_and_doping():
+    ens = eng.Ensemble(4, 8, 10, 1000)
+    fb = eng.FrameBatch(ens, 2, 100).generate_graphs(1).generate_erasures([0.3, 0.48], 2, doping_points=[4])
+    er = fb.erasures_host()
+    assert er.shape == (2, 100, ens.n)
+    assert not er[:, :, 4000:5000].any()                                   # hard-doped position is known
+    keep = np.r_[0:4000, 5000:10000]
+    assert abs(er[0][:, keep].mean() - 0.3) < 0.005 and abs(er[1][:, keep].mean() - 0.48) < 0.005
+    fb.generate_erasures(0.5, 2, doping_points={2: 0.25})
+    er = fb.erasures_host()
+    assert not er[:, :, 2000:2250].any() and er[:, :, 2250:3000].any()      # soft doping: first int(alpha*M) VNs
+    a = eng.FrameBatch(ens, 1, 100).generate_erasures(0.4, 9, first_graph_id=1).erasures_host()
+    b = eng.FrameBatch(ens, 2, 100).generate_erasures(0.4, 9, first_graph_id=0).erasures_host()
+    assert (a[0] == b[1]).all()                                            # realisations depend on global ids only
