@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 DV, DC, L, M = 4, 8, 50, 10000
 EPS_SWEEP = [0.46, 0.47, 0.48, 0.49]
-N_WORDS = 8
+N_WORDS = 16
 FRAMES_PER_GRAPH = 64 * N_WORDS
 E_EDGES = L * M * DV
 N_VNS = L * M
