@@ -311,12 +311,12 @@ def run_ours(args):
                 traffic = None
         if vn_t > 0 and cn_t > 0:
             ach = vn_b / vn_t / 1e9
-            roof = {"bound": "hbm", "kernel": "bp_vn_sweep_kernel<4,false,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "bp_vn_wave_kernel<4,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "launches_sampled": len(s_idx), "avg_launch_ms": 1e3 * vn_t / max(1, len(s_idx)),
                     "algorithmic_bytes": "(2E+n)/8 B per active frame per launch (reads E c2v bits + n channel bits, writes E v2c bits)"}
             ach_c = cn_b / cn_t / 1e9
-            kernels = {"bp_cn_sweep_kernel<8,false,false>": {"achieved": ach_c, "frac": ach_c / peak, "unit": "GB/s",
+            kernels = {"bp_cn_wave_kernel<8,false>": {"achieved": ach_c, "frac": ach_c / peak, "unit": "GB/s",
                                                             "avg_launch_ms": 1e3 * cn_t / max(1, len(s_idx)),
                                                             "algorithmic_bytes": "2E/8 B per active frame per launch"},
                        "both_sweeps": {"achieved": (cn_b + vn_b) / (cn_t + vn_t) / 1e9,
