@@ -4,8 +4,10 @@
     python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...   the reference's CPU decoder on the host cores
 
-A *step* decodes one batch: 4 graph realisations (one per eps of the 0.46..0.49 sweep of BASELINE config 2) x 512
-frames each, full BP with unlimited iterations until every frame has stalled or finished.  Throughput counts USEFUL
+A *step* decodes 4 graph realisations (one per eps of the 0.46..0.49 sweep of BASELINE config 2) x B frames each
+(default B = 4096, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
+or finished.  Default mode "stream": a lane whose frame has stopped is re-armed with the graph's next channel
+realisation (scldpc_bp_stream); mode "batch": B = lanes, every lane decodes one frame (scldpc_bp_full).  Throughput counts USEFUL
 work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same formula as for the CPU
 (SURVEY.md section 8d); iterations a finished frame rides along for do not count.
 
@@ -36,7 +38,8 @@ FRAMES_PER_GRAPH = 64 * N_WORDS
 E_EDGES = L * M * DV
 N_VNS = L * M
 WORKLOAD = ("full BP unlimited iterations, (4,8) SC-LDPC terminated L=50 M=10000, BEC eps sweep "
-            "{0.46,0.47,0.48,0.49}: 4 graphs x 512 frames per step")
+            "{0.46,0.47,0.48,0.49}: 4 graphs x B frames per step")
+FRAMES_PER_STREAM = 4096
 CAP_LO = 2   # reference arm: iterations of the shorter of the two capped runs
 METRIC = "edge-updates/s (frames/s alongside), (4,8) SC-LDPC L=50 M=10000 BEC BP"
 
@@ -207,17 +210,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
     ens = eng.Ensemble(DV, DC, L, M)
+    stream_mode = args.mode == "stream"
+    lanes = FRAMES_PER_GRAPH                                     # bit-sliced lanes per graph
+    B = args.frames_per_graph if stream_mode else lanes         # frames decoded per graph and step
     G = len(EPS_SWEEP) * args.graphs_per_eps
     eps = [e for e in EPS_SWEEP for _ in range(args.graphs_per_eps)]
+    eps_arr = np.asarray(eps, np.float64)
 
     # two resident batches, alternated, each an independent draw: graph ids are global, so the realisations (and
     # therefore the results) do not depend on how many GPUs share the job
     batches = []
     for bidx in range(2):
         gid0 = (rank * 2 + bidx) * G
-        fb = eng.FrameBatch(ens, G, FRAMES_PER_GRAPH, N_WORDS, device=dev)
+        fb = eng.FrameBatch(ens, G, lanes, N_WORDS, device=dev)
         fb.generate_graphs(seed=args.seed, first_graph_id=gid0)
-        fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid0)
+        if not stream_mode:
+            fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid0)
+        fb.gid0 = gid0
         batches.append(fb)
     torch.cuda.synchronize()
 
@@ -225,12 +234,14 @@ def run_ours(args):
 
     def step(i, acc=True):
         fb = batches[i % 2]
-        res, erased, rows, launched = eng.decode_bp_full(fb, eng.UNLIMITED, True, collect=False)
+        if stream_mode:
+            res, _ = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=fb.gid0, collect=False)
+            it, resid = res[0].to(torch.int64), res[1].to(torch.int64)
+        else:
+            res, erased, rows, launched = eng.decode_bp_full(fb, eng.UNLIMITED, True, collect=False)
+            it, resid = res[0, :, :lanes].to(torch.int64), res[1, :, :lanes].to(torch.int64)
         if acc:
-            it = res[0, :, :FRAMES_PER_GRAPH].to(torch.int64)
-            resid = res[1, :, :FRAMES_PER_GRAPH].to(torch.int64)
             counters.add_(torch.stack([it.sum(), torch.tensor(it.numel(), device=dev), (resid > 0).sum(), resid.sum()]))
-        return res
 
     def barrier():
         if world > 1:
@@ -242,29 +253,28 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: K steps, device-resident inputs ---------------------------------------------------------
-    sample_every = 8
-    _lib.check(lib.scldpc_profile_begin(sample_every, 8192))
+    sample_every = 7        # co-prime with the harvest period (16), so sampled launches are representative
+    _lib.check(lib.scldpc_profile_begin(sample_every, 16384))
     lib.scldpc_launch_count(1)
     clocks = ClockSampler(local_rank)
-    step_iters = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for i in range(args.steps):
-        r = step(i)
-        step_iters.append(r[0])
+        step(i)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib.scldpc_launch_count(1)
     clk = clocks.stop()
-    cap = 8192
+    cap = 16384
     ns = ctypes.c_int(0)
     it_idx = (ctypes.c_int * cap)()
     cn_ms = (ctypes.c_float * cap)()
     vn_ms = (ctypes.c_float * cap)()
     _lib.check(lib.scldpc_profile_end(ctypes.byref(ns), it_idx, cn_ms, vn_ms, cap))
 
+    local_frame_iters = int(counters[0].item())
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = counters.clone()
     if world > 1:
@@ -274,9 +284,11 @@ def run_ours(args):
     frame_iters, frames, ferr, berr = (int(x) for x in tot.tolist())
     value = frame_iters * 2.0 * E_EDGES / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel from the sampled launches -------------------------------------------
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    # algorithmic bytes per launch = useful frame-iterations of the timed region / sweeps launched x bytes per
+    # frame-iteration of that sweep; average launch duration from the CUDA-event samples (every 7th iteration)
     roof = kernels = None
-    if rank == 0:
+    if rank == 0 and ns.value > 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -284,24 +296,13 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # active frames of the sampled launch = frames of that step whose iteration count exceeds the sampled index
-        its = [x[:, :FRAMES_PER_GRAPH].cpu().numpy().astype(np.int64) for x in step_iters]
-        s_idx, step_no, prev = [], -1, 1 << 30
-        for k in range(ns.value):
-            if it_idx[k] <= prev and it_idx[k] == 0:
-                step_no += 1
-            prev = it_idx[k]
-            s_idx.append((step_no, it_idx[k]))
-        cn_b = vn_b = 0.0
-        cn_t = vn_t = 0.0
-        for k, (sn, t) in enumerate(s_idx):
-            if sn < 0 or sn >= len(its):
-                continue
-            active = int((its[sn] > t).sum())
-            cn_b += active * (2 * E_EDGES) / 8.0
-            vn_b += active * (2 * E_EDGES + N_VNS) / 8.0
-            cn_t += cn_ms[k] * 1e-3
-            vn_t += vn_ms[k] * 1e-3
+        n_s = ns.value
+        cn_avg = float(np.mean(cn_ms[:n_s])) * 1e-3
+        vn_avg = float(np.mean(vn_ms[:n_s])) * 1e-3
+        n_iter_launches = n_s * sample_every                      # iterations launched by this rank in the timed region
+        fi_per_launch = local_frame_iters / max(1, n_iter_launches)
+        cn_bytes = fi_per_launch * (2 * E_EDGES) / 8.0
+        vn_bytes = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
@@ -309,33 +310,48 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get("vn_sweep_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        if vn_t > 0 and cn_t > 0:
-            ach = vn_b / vn_t / 1e9
-            roof = {"bound": "hbm", "kernel": "bp_vn_wave_kernel<4,false>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                    "launches_sampled": len(s_idx), "avg_launch_ms": 1e3 * vn_t / max(1, len(s_idx)),
-                    "algorithmic_bytes": "(2E+n)/8 B per active frame per launch (reads E c2v bits + n channel bits, writes E v2c bits)"}
-            ach_c = cn_b / cn_t / 1e9
-            kernels = {"bp_cn_wave_kernel<8,false>": {"achieved": ach_c, "frac": ach_c / peak, "unit": "GB/s",
-                                                            "avg_launch_ms": 1e3 * cn_t / max(1, len(s_idx)),
-                                                            "algorithmic_bytes": "2E/8 B per active frame per launch"},
-                       "both_sweeps": {"achieved": (cn_b + vn_b) / (cn_t + vn_t) / 1e9,
-                                       "frac": (cn_b + vn_b) / (cn_t + vn_t) / 1e9 / peak, "unit": "GB/s"}}
+        vn_name = "bp_vn_stream_kernel<4>" if stream_mode else "bp_vn_wave_kernel<4,false>"
+        ach = vn_bytes / vn_avg / 1e9
+        roof = {"bound": "hbm", "kernel": vn_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "launches_sampled": n_s, "avg_launch_ms": 1e3 * vn_avg,
+                "frame_iterations_per_launch": fi_per_launch,
+                "algorithmic_bytes": "(2E+n)/8 B per useful frame-iteration (reads E c2v bits + n channel bits, writes E v2c bits)"}
+        ach_c = cn_bytes / cn_avg / 1e9
+        kernels = {"bp_cn_wave_kernel<8,false>": {"achieved": ach_c, "frac": ach_c / peak, "unit": "GB/s", "avg_launch_ms": 1e3 * cn_avg,
+                                                  "algorithmic_bytes": "2E/8 B per useful frame-iteration"},
+                   "both_sweeps": {"achieved": (cn_bytes + vn_bytes) / (cn_avg + vn_avg) / 1e9,
+                                   "frac": (cn_bytes + vn_bytes) / (cn_avg + vn_avg) / 1e9 / peak, "unit": "GB/s"}}
 
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
-    e2e = None
     h_vn = [fb.vn_cn.cpu().pin_memory() for fb in batches]
-    h_ch = [fb.chan.cpu().pin_memory() for fb in batches]
-    lanes = FRAMES_PER_GRAPH
-    outs = [torch.zeros((G, lanes), dtype=torch.int32).pin_memory() for _ in range(5)]
     dims = batches[0].dims
-    flags = _lib.F_TERMINATED | _lib.F_CHAN_PACKED
+    if stream_mode:
+        outs = [torch.zeros((G, B), dtype=torch.int32).pin_memory() for _ in range(5)]
+        cfgs = []
+        for fb in batches:
+            cfgs.append(_lib.StreamCfg(B, 16, _lib.F_TERMINATED, 0, 0, eps_arr.ctypes.data_as(ctypes.c_void_p).value, None, None, None,
+                                       args.seed + 1, fb.gid0))
+        h2d = int(h_vn[0].numel() * 4)
+        d2h = int(5 * G * B * 4)
+        api = "scldpc_stream_host (graph tables in pinned host memory; channel realisations drawn on the device)"
 
-    def e2e_step(i):
-        _lib.check(lib.scldpc_decode_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[i % 2].data_ptr()),
-                                          ctypes.c_void_p(h_ch[i % 2].data_ptr()), 0, 0, 0, flags,
-                                          *[ctypes.c_void_p(o.data_ptr()) for o in outs], None, None, None, 0))
-        return int(outs[0].sum().item())
+        def e2e_step(i):
+            _lib.check(lib.scldpc_stream_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[i % 2].data_ptr()), ctypes.byref(cfgs[i % 2]),
+                                              *[ctypes.c_void_p(o.data_ptr()) for o in outs], None))
+            return int(outs[0].sum().item())
+    else:
+        h_ch = [fb.chan.cpu().pin_memory() for fb in batches]
+        outs = [torch.zeros((G, lanes), dtype=torch.int32).pin_memory() for _ in range(5)]
+        flags = _lib.F_TERMINATED | _lib.F_CHAN_PACKED
+        h2d = int(h_vn[0].numel() * 4 + h_ch[0].numel() * 8)
+        d2h = int(6 * G * lanes * 4)
+        api = "scldpc_decode_host (graph tables + bit-sliced channel words in pinned host memory)"
+
+        def e2e_step(i):
+            _lib.check(lib.scldpc_decode_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[i % 2].data_ptr()),
+                                              ctypes.c_void_p(h_ch[i % 2].data_ptr()), 0, 0, 0, flags,
+                                              *[ctypes.c_void_p(o.data_ptr()) for o in outs], None, None, None, 0))
+            return int(outs[0].sum().item())
 
     for i in range(min(2, args.warmup)):
         e2e_step(i)
@@ -352,19 +368,19 @@ def run_ours(args):
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
         dist.all_reduce(ei, op=dist.ReduceOp.SUM)
     e2e = {"value": float(ei.item()) * 2.0 * E_EDGES / float(et.item()), "unit": "edge-updates/s",
-           "frames_per_s": world * args.steps * G * FRAMES_PER_GRAPH / float(et.item()),
-           "h2d_bytes_per_step": int(h_vn[0].numel() * 4 + h_ch[0].numel() * 8),
-           "d2h_bytes_per_step": int(6 * G * 64 * N_WORDS * 4),
-           "api": "scldpc_decode_host (graph tables + bit-sliced channel words in pinned host memory)"}
+           "frames_per_s": world * args.steps * G * B / float(et.item()),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api}
 
     if rank == 0:
-        ws_mb = batches[0].workspace(_lib.F_TERMINATED).numel() / 2 ** 20
+        need = lib.scldpc_bp_stream_workspace_bytes(ctypes.byref(dims)) if stream_mode else batches[0].workspace(_lib.F_TERMINATED).numel()
+        ws_mb = need / 2 ** 20
         line = {
             "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (64 bit-sliced frames per word)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": G * FRAMES_PER_GRAPH, "n_words": N_WORDS,
-                       "l2": f"inputs larger than L2: {ws_mb:.0f} MB of messages per batch, two batches alternated",
+            "config": {"workload": WORKLOAD.replace("B frames", f"{B} frames"), "mode": args.mode, "frames_per_step_per_gpu": G * B,
+                       "lanes_per_graph": lanes, "n_words": N_WORDS,
+                       "l2": f"inputs larger than L2: {ws_mb:.0f} MB of decoder state per batch, two batches alternated",
                        "seed": args.seed},
             "frames_per_s": frames / (ms * 1e-3),
             "frame_iterations_per_s": frame_iters / (ms * 1e-3),
@@ -390,11 +406,13 @@ def main():
     ap.add_argument("--graphs-per-eps", type=int, default=1)
     ap.add_argument("--sample-iters", type=int, default=10, help="reference arm: flooding iterations per sampled frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--n-words", type=int, default=N_WORDS, help="64-bit lane words per node (frames per graph / 64)")
+    ap.add_argument("--n-words", type=int, default=N_WORDS, help="64-bit lane words per node (lanes per graph / 64)")
+    ap.add_argument("--mode", default="stream", choices=["stream", "batch"],
+                    help="stream: lane recycling over --frames-per-graph frames per graph; batch: one frame per lane")
+    ap.add_argument("--frames-per-graph", type=int, default=FRAMES_PER_STREAM)
     args = ap.parse_args()
     N_WORDS = args.n_words
     FRAMES_PER_GRAPH = 64 * N_WORDS
-    WORKLOAD = WORKLOAD.replace("512 frames", f"{FRAMES_PER_GRAPH} frames")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

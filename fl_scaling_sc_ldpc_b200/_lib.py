@@ -24,6 +24,7 @@ EXPORTS = [
     "scldpc_last_error", "scldpc_version", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
     "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_decode_host",
+    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host",
     "scldpc_peel_workspace_bytes", "scldpc_peel_trajectories", "scldpc_peel_variance_accumulate", "scldpc_philox_picks",
     "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end", "scldpc_bp_sweep_stats",
 ]
@@ -49,6 +50,17 @@ class BpOut(ctypes.Structure):
                 ("max_rows", ctypes.c_int32)]
 
 
+class StreamCfg(ctypes.Structure):
+    _fields_ = [("frames_per_graph", ctypes.c_int32), ("harvest_every", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("n_doped", ctypes.c_int32), ("n_soft", ctypes.c_int32), ("eps_host", ctypes.c_void_p),
+                ("doped_pos_host", ctypes.c_void_p), ("soft_pos_host", ctypes.c_void_p), ("soft_count_host", ctypes.c_void_p),
+                ("seed", ctypes.c_uint64), ("first_graph_id", ctypes.c_uint64)]
+
+
+class StreamOut(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("iters_dev", "residual_dev", "blocks_err_dev", "erasures_exp_dev", "blocks_err_exp_dev")]
+
+
 _lib = None
 
 
@@ -69,6 +81,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.scldpc_last_error.restype = ctypes.c_char_p
         L.scldpc_bp_workspace_bytes.restype = ctypes.c_size_t
+        L.scldpc_bp_stream_workspace_bytes.restype = ctypes.c_size_t
         L.scldpc_graph_generate_scratch_bytes.restype = ctypes.c_size_t
         L.scldpc_launch_count.restype = ctypes.c_longlong
         L.scldpc_peel_workspace_bytes.restype = ctypes.c_size_t

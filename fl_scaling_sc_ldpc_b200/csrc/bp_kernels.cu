@@ -328,10 +328,13 @@ __global__ void __launch_bounds__(256) bp_pos_count_kernel(BpParams p)
     __syncthreads();
     const u128 *x = p.x + ((size_t)g * p.n + (size_t)pos * p.vns_pos) * ch;
     const int items = p.vns_pos * ch;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += gridDim.x * blockDim.x) {
-        const u128 xv = x[idx];
-        if (nz(xv)) sparse_count(s_cnt, (idx & (ch - 1)) * 128, xv);
-    }
+    // a thread keeps its chunk (blockDim and the stride are multiples of ch); chunks without a selected lane are skipped
+    const u128 mask = p.lane_mask ? reinterpret_cast<const u128 *>(p.lane_mask)[g * ch + (threadIdx.x & (ch - 1))] : ones128();
+    if (nz(mask))
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += gridDim.x * blockDim.x) {
+            const u128 xv = x[idx] & mask;
+            if (nz(xv)) sparse_count(s_cnt, (idx & (ch - 1)) * 128, xv);
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
         if (s_cnt[i]) atomicAdd(p.pos_cnt + ((size_t)g * p.L + pos) * p.lanes + i, s_cnt[i]);
@@ -348,9 +351,11 @@ __global__ void __launch_bounds__(256) bp_pairs_kernel(BpParams p)
     const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * DV;
     const int32_t *cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
     const long long items = (long long)p.n << p.chunk_shift;
+    const u128 mask = p.lane_mask ? reinterpret_cast<const u128 *>(p.lane_mask)[g * ch + (threadIdx.x & (ch - 1))] : ones128();
+    if (!nz(mask)) return;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (long long)gridDim.x * blockDim.x) {
         const int a = (int)(idx >> p.chunk_shift), k = (int)(idx & (ch - 1));
-        const u128 xa = x[(size_t)a * ch + k];
+        const u128 xa = x[(size_t)a * ch + k] & mask;
         if (!nz(xa)) continue;
         u128 cand = xa;
         for (int i = 0; i < DV && nz(cand); i++) {
@@ -497,6 +502,26 @@ int bp_launch_iteration(int dv, int dc, const BpParams &p, bool traj, bool freez
     return 0;
 }
 
+template <int DV, int DC>
+static void launch_count_pairs(const BpParams &p, cudaStream_t st)
+{
+    int bx = (p.vns_pos * p.chunks + 255) / 256;
+    if (bx > 8) bx = 8;
+    g_prof.launches += 2;
+    bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
+    dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, 4);
+    bp_pairs_kernel<DV, DC><<<gp, 256, 0, st>>>(p);
+}
+
+// erased VNs per (position, lane) and accepted size-two stopping sets, restricted to p.lane_mask
+int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st)
+{
+#define CALL_CP(A, B) launch_count_pairs<A, B>(p, st)
+    SCLDPC_DISPATCH(dv, dc, CALL_CP);
+#undef CALL_CP
+    return 0;
+}
+
 int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, cudaStream_t st)
 {
 #define CALL_FIN(A, B) launch_finalize<A, B>(p, o, st)
@@ -510,6 +535,12 @@ void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_fra
     dim3 g((unsigned)(num_sms() * 4 / (p.G > 0 ? p.G : 1) + 1), (unsigned)p.G);
     g_prof.launches += 2;
     bp_init_messages_kernel<<<g, 256, 0, st>>>(p, dv, dc, trajectory);
+    bp_init_ctrl_kernel<<<p.G, 256, 0, st>>>(p, n_frames);
+}
+
+void bp_launch_init_ctrl_only(const BpParams &p, int n_frames, cudaStream_t st)
+{
+    g_prof.launches += 1;
     bp_init_ctrl_kernel<<<p.G, 256, 0, st>>>(p, n_frames);
 }
 

@@ -302,6 +302,211 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// frame streams: lane recycling
+// ------------------------------------------------------------------------------------------------------------
+// Frames that share a word finish at very different iterations (eps = 0.49, M = 10000: mean 794, max 1747), and a
+// word costs the same whether one or all of its 64 lanes are still decoding.  In stream mode a graph realisation
+// decodes a stream of B frames: when a lane's frame stops, its results are harvested and the lane is re-armed with
+// the next channel realisation, so (almost) every lane of every word does useful work in every sweep.
+//   VN sweep: for lanes in arm_mask the outgoing messages, x and y are (re)initialised from the new frame's channel
+//             bits (drawn in place, channel_draw) instead of being computed; such lanes start iterating next sweep.
+//   retire  : per-lane iteration counters; stopped lanes go to done_mask and stay untouched (their x is a fixed point).
+//   harvest : every few iterations the finalisation kernels run on done_mask only, results are stored under the
+//             frame id, and the freed lanes get the next frame ids in ascending lane order (deterministic).
+// Only unlimited-iteration decoding streams (a capped frame would keep changing while it waits for the harvest).
+template <int DV>
+__global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
+    __shared__ int s_last;
+    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_new[threadIdx.x] = 0; s_er[threadIdx.x] = 0; }
+    __syncthreads();
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const u128 arm = reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k];
+    const bool lane_work = nz(act | arm);
+    u128 acc_new = zero128(), acc_er = zero128();   // every position is swept, so "an erased VN is left" is a plain OR
+    const u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * p.dc * ch;
+    u128 *__restrict__ v2c = p.v2c + (size_t)g * (p.E + 1) * ch;
+    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u128 *__restrict__ y = p.y + (size_t)g * p.n * ch;
+    const int32_t *__restrict__ vn_slot = p.vn_slot + (size_t)g * p.n * DV;
+    const int items = p.n << p.chunk_shift;
+    const int stride = gridDim.x * blockDim.x;
+    const u64 thr = nz(arm) ? p.thr[g] : 0ull;
+    const uint64_t gid = p.first_graph + (uint64_t)g;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
+        const int idx = base + (threadIdx.x & 31);
+        const bool work = lane_work && idx < items;
+        u128 changed = zero128(), xn = zero128(), yn = zero128(), xo = zero128(), yo = zero128();
+        u128 out[DV];
+        const int v = idx >> p.chunk_shift;
+        if (work) {
+            int s[DV];
+            load_row<DV>(vn_slot + (size_t)v * DV, s);
+            u128 in[DV];
+#pragma unroll
+            for (int i = 0; i < DV; i++) in[i] = ld_stream(c2v + (size_t)s[i] * ch + k);
+            xo = x[(size_t)v * ch + k];
+            yo = y[(size_t)v * ch + k];
+            u128 acc = yo;
+#pragma unroll
+            for (int i = 0; i < DV; i++) { out[i] = acc; acc &= in[i]; }
+            xn = acc;
+            acc = ones128();
+#pragma unroll
+            for (int i = DV - 1; i >= 0; i--) { out[i] &= acc; acc &= in[i]; }
+#pragma unroll
+            for (int i = 0; i < DV; i++) yn |= out[i];
+            if (nz(arm)) {
+                // new frames: Lji = channel value on every edge (BP_FULL.c:913-917), previous decision "all erased"
+                const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
+                u128 cw = zero128();
+                for (int half = 0; half < 2; half++) {
+                    u64 m = half ? arm.y : arm.x, w = 0;
+                    while (m) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const int fr = p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
+                        if (!forced && (u64)channel_draw(p.seed, gid, (uint32_t)fr, (uint32_t)v) < thr) w |= 1ull << b;
+                    }
+                    if (half) cw.y = w; else cw.x = w;
+                }
+#pragma unroll
+                for (int i = 0; i < DV; i++) out[i] = sel(arm, cw, out[i]);
+                xn = xn | arm;
+                yn = sel(arm, cw, yn);
+            }
+            changed = make_u128((((xn.x ^ xo.x) | (yn.x ^ yo.x)) & act.x) | arm.x, (((xn.y ^ xo.y) | (yn.y ^ yo.y)) & act.y) | arm.y);
+        }
+        unsigned flag = nz(changed) ? 1u : 0u;
+        for (int o = 1; o < ch; o <<= 1) flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+        if (work) {
+            if (flag) {
+                u128 *dst = v2c + ((size_t)v * DV) * ch + k;
+#pragma unroll
+                for (int i = 0; i < DV; i++) dst[(size_t)i * ch] = out[i];
+            }
+            if (neq(xn, xo)) x[(size_t)v * ch + k] = xn;
+            if (neq(yn, yo)) y[(size_t)v * ch + k] = yn;
+            acc_new |= xo & ~xn & act;
+            acc_er |= xn & act;
+        }
+    }
+    acc_new = warp_or_same_chunk(acc_new, ch);
+    acc_er = warp_or_same_chunk(acc_er, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
+        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
+        if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
+        if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
+        if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- end of the iteration for graph g ----
+    __shared__ u64 s_stop[SCLDPC_MAX_WORDS], s_act[SCLDPC_MAX_WORDS];
+    const int W = p.W;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        const u64 er = ld_cg(p.any_er + g * W + w);
+        p.any_er[g * W + w] = 0;
+        const u64 a = p.active[g * W + w];
+        const u64 nw = ld_cg(p.any_new + g * W + w);
+        const u64 stop = a & (~er | ~nw);                      // NumErasures == 0  ||  == NumErasuresPrec
+        s_stop[w] = stop;
+        s_act[w] = a;
+        p.active[g * W + w] = (a & ~stop) | p.arm_mask[g * W + w];   // armed lanes start iterating with the next sweep
+        p.arm_mask[g * W + w] = 0;
+        p.done_mask[g * W + w] |= stop;
+        p.any_new[g * W + w] = 0;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_act[w] >> b) & 1ull) p.lane_iter[g * p.lanes + l] += 1;
+    }
+    if (threadIdx.x == 0) p.ticket[g] = 0;
+}
+
+// harvest step 3 (one block per graph): results of the lanes in done_mask, then re-arm them with the next frame ids
+__global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
+{
+    const int g = blockIdx.x, L = p.L, W = p.W, B = p.frames_per_graph;
+    if (ld_cg(p.alive + g) == 0) return;
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        if (!((p.done_mask[g * W + (l >> 6)] >> (l & 63)) & 1ull)) continue;
+        const int fr = p.lane_frame[g * p.lanes + l];
+        int residual = 0, blocks = 0, e_exp = 0, b_exp = 0, first_done = 0;
+        for (int q = 0; q < L; q++) {
+            const size_t o = ((size_t)g * L + q) * p.lanes + l;
+            const int plain = p.pos_cnt[o], ex = plain - 2 * p.pos_pairs[o];
+            p.pos_cnt[o] = 0;
+            p.pos_pairs[o] = 0;
+            residual += plain;
+            if (plain > 0) blocks++;
+            if (ex > 0 && (exp_all || !first_done)) { first_done = 1; e_exp += ex; b_exp++; }
+        }
+        if (fr >= 0 && fr < B) {
+            const size_t o = (size_t)g * B + fr;
+            p.s_iters[o] = p.lane_iter[g * p.lanes + l];
+            p.s_residual[o] = residual;
+            p.s_blocks_err[o] = blocks;
+            p.s_erasures_exp[o] = e_exp;
+            p.s_blocks_err_exp[o] = b_exp;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int next = p.next_frame[g];
+        u64 any = 0;
+        for (int w = 0; w < W; w++) {
+            u64 d = p.done_mask[g * W + w], armw = 0;
+            while (d) {
+                const int b = __ffsll((long long)d) - 1;
+                d &= d - 1;
+                const int l = w * 64 + b;
+                if (next < B) { p.lane_frame[g * p.lanes + l] = next++; p.lane_iter[g * p.lanes + l] = 0; armw |= 1ull << b; }
+                else p.lane_frame[g * p.lanes + l] = -1;
+            }
+            p.done_mask[g * W + w] = 0;
+            p.arm_mask[g * W + w] = armw;
+            any |= armw | p.active[g * W + w];
+        }
+        p.next_frame[g] = next;
+        if (!any) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
+    }
+}
+
+__global__ void bp_stream_init_kernel(BpParams p, int n_lanes_used)
+{
+    const int g = blockIdx.x;
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        p.lane_frame[g * p.lanes + l] = -1;
+        p.lane_iter[g * p.lanes + l] = 0;
+    }
+    for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
+        const int lo = w * 64;
+        // every usable lane starts "done" with no frame: the first harvest only arms them
+        p.done_mask[g * p.W + w] = (n_lanes_used >= lo + 64) ? ~0ull : (n_lanes_used <= lo ? 0ull : ((1ull << (n_lanes_used - lo)) - 1ull));
+        p.arm_mask[g * p.W + w] = 0;
+        p.active[g * p.W + w] = 0;
+    }
+    if (threadIdx.x == 0) p.next_frame[g] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 template <typename K>
@@ -359,6 +564,58 @@ int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaS
     else if (dv == 4 && dc == 12) launch_wave_iteration<4, 12>(p, traj, st, waves);
     else return -1;
     return 0;
+}
+
+template <int DV, int DC>
+static void launch_stream_iteration(const BpParams &p, cudaStream_t st)
+{
+    const int block = 256;
+    static int res_cn = 0, res_vn = 0;
+    if (!res_cn) {
+        res_cn = resident_blocks(bp_cn_wave_kernel<DC, false>, block);
+        res_vn = resident_blocks(bp_vn_stream_kernel<DV>, block);
+    }
+    auto grid = [&](int resident, long long items_per_graph) {
+        long long need = (items_per_graph + block - 1) / block;
+        long long gx = need < resident ? need : resident;
+        return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+    };
+    dim3 gc = grid(res_cn, (long long)p.cn_pos_lim * p.cns_pos << p.chunk_shift);
+    dim3 gv = grid(res_vn, (long long)p.n << p.chunk_shift);
+    const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
+    cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
+    if (sample) cudaEventRecord(ev[0], st);
+    g_prof.launches += 2;
+    bp_cn_wave_kernel<DC, false><<<gc, block, 0, st>>>(p);
+    if (sample) cudaEventRecord(ev[1], st);
+    bp_vn_stream_kernel<DV><<<gv, block, 0, st>>>(p);
+    if (sample) {
+        cudaEventRecord(ev[2], st);
+        g_prof.iter_idx[g_prof.n_samples++] = p.iter;
+    }
+}
+
+int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, cudaStream_t st)
+{
+    if (dv == 4 && dc == 8) launch_stream_iteration<4, 8>(p, st);
+    else if (dv == 3 && dc == 6) launch_stream_iteration<3, 6>(p, st);
+    else if (dv == 5 && dc == 10) launch_stream_iteration<5, 10>(p, st);
+    else if (dv == 3 && dc == 9) launch_stream_iteration<3, 9>(p, st);
+    else if (dv == 4 && dc == 12) launch_stream_iteration<4, 12>(p, st);
+    else return -1;
+    return 0;
+}
+
+void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    bp_stream_init_kernel<<<p.G, 256, 0, st>>>(p, n_lanes_used);
+}
+
+void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    bp_stream_harvest_kernel<<<p.G, 256, 0, st>>>(p, exp_all);
 }
 
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st)

@@ -16,15 +16,20 @@ int bp_launch_iteration(int dv, int dc, const BpParams &p, bool traj, bool freez
 int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, cudaStream_t st);
 void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_frames, cudaStream_t st);
 void bp_launch_window_begin(const BpParams &p, int n_frames, cudaStream_t st);
+void bp_launch_init_ctrl_only(const BpParams &p, int n_frames, cudaStream_t st);
 int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
+int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, cudaStream_t st);
+void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
+void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
+int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
 int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge, int32_t *scratch, int *err_dev, int G,
                        int n, int nk, int dv, int dc, cudaStream_t st);
 int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
                    uint64_t first_graph, int tail_biting, cudaStream_t st);
 size_t graph_generate_scratch_words(int G, int L, int cns_pos, int dv, int dc, int tail_biting);
 void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
-                      uint64_t seed, uint64_t first_graph, cudaStream_t st);
+                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st);
 void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
 void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
 void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
@@ -138,6 +143,14 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.vn_list = c.take<int>(G * d->L);
     q.n_list = c.take<int>(G * 2);
     q.swept = c.take<long long>(G * 2);
+    q.arm_mask = c.take<u64>(G * W);
+    q.done_mask = c.take<u64>(G * W);
+    q.lane_frame = c.take<int>(G * lanes);
+    q.lane_iter = c.take<int>(G * lanes);
+    q.next_frame = c.take<int>(G);
+    q.thr = c.take<u64>(G);
+    q.known = c.take<int32_t>(d->L);
+    if (flags & SCLDPC_F_STREAM) q.x = c.take<u128>(G * n * ch);      // stream mode owns its decision plane
     if (p) *p = q;
     return c.off;
 }
@@ -246,34 +259,44 @@ extern "C" size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, in
     return sizeof(u64) * graph_generate_scratch_words(d->n_graphs, d->L, d->cns_pos, d->dv, d->dc, tail_biting);
 }
 
+// doping description -> per-position count of leading VNs that are known (hard: all of them; soft: int(alpha*M))
+static int build_known(const scldpc_dims_t *d, const int32_t *doped_pos_host, int n_doped, const int32_t *soft_pos_host,
+                       const int32_t *soft_count_host, int n_soft, std::vector<int32_t> *known)
+{
+    known->assign(d->L, 0);
+    for (int i = 0; i < n_doped; i++) {
+        if (doped_pos_host[i] < 0 || doped_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "doped position out of range");
+        (*known)[doped_pos_host[i]] = d->vns_pos;
+    }
+    for (int i = 0; i < n_soft; i++) {
+        if (soft_pos_host[i] < 0 || soft_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "soft-doped position out of range");
+        int c = soft_count_host[i] < 0 ? 0 : (soft_count_host[i] > d->vns_pos ? d->vns_pos : soft_count_host[i]);
+        if (c > (*known)[soft_pos_host[i]]) (*known)[soft_pos_host[i]] = c;
+    }
+    return 0;
+}
+
 extern "C" int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
                                        int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
-                                       uint64_t seed, uint64_t first_graph_id, void *stream)
+                                       uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, void *stream)
 {
     int rc = check_dims(d);
     if (rc) return rc;
     if (!chan_dev) return fail(SCLDPC_EINVAL, "chan_dev is NULL");
     if (!(eps >= 0.0 && eps <= 1.0)) return fail(SCLDPC_EINVAL, "eps must be in [0,1]");
+    if (first_frame_id & 3u) return fail(SCLDPC_EINVAL, "first_frame_id must be a multiple of 4");
     if ((rc = have_device())) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int32_t *known_dev = nullptr;
     if (n_doped > 0 || n_soft > 0) {
-        std::vector<int32_t> known(d->L, 0);
-        for (int i = 0; i < n_doped; i++) {
-            if (doped_pos_host[i] < 0 || doped_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "doped position out of range");
-            known[doped_pos_host[i]] = d->vns_pos;
-        }
-        for (int i = 0; i < n_soft; i++) {
-            if (soft_pos_host[i] < 0 || soft_pos_host[i] >= d->L) return fail(SCLDPC_EINVAL, "soft-doped position out of range");
-            int c = soft_count_host[i] < 0 ? 0 : (soft_count_host[i] > d->vns_pos ? d->vns_pos : soft_count_host[i]);
-            if (c > known[soft_pos_host[i]]) known[soft_pos_host[i]] = c;
-        }
+        std::vector<int32_t> known;
+        if ((rc = build_known(d, doped_pos_host, n_doped, soft_pos_host, soft_count_host, n_soft, &known))) return rc;
         CU(cudaMallocAsync(&known_dev, sizeof(int32_t) * d->L, st));
         CU(cudaMemcpyAsync(known_dev, known.data(), sizeof(int32_t) * d->L, cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));   // `known` leaves scope below
     }
     channel_generate(reinterpret_cast<u64 *>(chan_dev), d->n_graphs, d->L * d->vns_pos, d->n_words, d->n_frames, d->vns_pos,
-                     known_dev, eps, seed, first_graph_id, st);
+                     known_dev, eps, seed, first_graph_id, first_frame_id, st);
     CU(cudaGetLastError());
     if (known_dev) CU(cudaFreeAsync(known_dev, st));
     return 0;
@@ -383,6 +406,113 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     bp_launch_finalize(d->dv, d->dc, p, fo, st);
     CU(cudaGetLastError());
     if (iters_launched_host) *iters_launched_host = launched;
+    return 0;
+}
+
+extern "C" size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d)
+{
+    if (check_dims(d)) return 0;
+    return carve(d, SCLDPC_F_STREAM, nullptr, nullptr);
+}
+
+// Full BP (unlimited iterations) over a stream of cfg->frames_per_graph frames per graph with lane recycling.
+extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b, const scldpc_stream_cfg_t *cfg,
+                                const scldpc_stream_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                                long long *iters_launched_host, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!degrees_supported(d->dv, d->dc)) return fail(SCLDPC_EINVAL, "(dv,dc)=(%d,%d) not instantiated", d->dv, d->dc);
+    if (!b || !b->vn_cn_dev || !b->vn_slot_dev || !b->cn_edge_dev) return fail(SCLDPC_EINVAL, "batch pointer is NULL");
+    if (!cfg || !cfg->eps_host || cfg->frames_per_graph < 1) return fail(SCLDPC_EINVAL, "bad stream configuration");
+    if (!out || !out->iters_dev || !out->residual_dev || !out->blocks_err_dev || !out->erasures_exp_dev || !out->blocks_err_exp_dev)
+        return fail(SCLDPC_EINVAL, "output pointer is NULL");
+    if (d->n_frames < 1) return fail(SCLDPC_EINVAL, "n_frames (lanes used per graph) must be >= 1");
+    if (d->L + d->dv - 1 > 1024) return fail(SCLDPC_EINVAL, "chain too long for stream mode");
+    if (!workspace_dev) return fail(SCLDPC_EINVAL, "workspace is NULL");
+    const size_t need = carve(d, SCLDPC_F_STREAM, nullptr, nullptr);
+    if (workspace_bytes < need) return fail(SCLDPC_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    if ((rc = have_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BpParams p;
+    carve(d, SCLDPC_F_STREAM, workspace_dev, &p);
+    p.dv = d->dv; p.dc = d->dc;
+    p.n = d->L * d->vns_pos; p.nk = (d->L + d->dv - 1) * d->cns_pos; p.E = p.n * d->dv;
+    p.L = d->L; p.vns_pos = d->vns_pos; p.cns_pos = d->cns_pos;
+    p.G = d->n_graphs; p.W = d->n_words; p.chunks = d->n_words / 2; p.lanes = 64 * d->n_words;
+    p.chunk_shift = 0;
+    while ((1 << p.chunk_shift) < p.chunks) p.chunk_shift++;
+    p.vn_cn = b->vn_cn_dev; p.vn_slot = b->vn_slot_dev; p.cn_edge = b->cn_edge_dev; p.chan = nullptr;
+    p.iters = p.lane_iter;                       // scratch for the shared control initialisation
+    p.rows = nullptr; p.max_rows = 0; p.row = -1;
+    const bool term = cfg->flags & SCLDPC_F_TERMINATED;
+    p.cn_pos_lim = term ? d->L + d->dv - 1 : d->L;
+    p.c0 = 0; p.c1 = p.cn_pos_lim * d->cns_pos; p.v0 = 0; p.v1 = p.n;
+    p.max_it = INT_MAX; p.first_iter = 0; p.stall_at_first = 1;
+    p.frames_per_graph = cfg->frames_per_graph; p.seed = cfg->seed; p.first_graph = cfg->first_graph_id;
+    p.s_iters = out->iters_dev; p.s_residual = out->residual_dev; p.s_blocks_err = out->blocks_err_dev;
+    p.s_erasures_exp = out->erasures_exp_dev; p.s_blocks_err_exp = out->blocks_err_exp_dev;
+    p.lane_mask = p.done_mask;
+    // per-graph channel thresholds and the doping profile
+    std::vector<u64> thr(d->n_graphs);
+    for (int g = 0; g < d->n_graphs; g++) {
+        const double e = cfg->eps_host[g];
+        if (!(e >= 0.0 && e <= 1.0)) return fail(SCLDPC_EINVAL, "eps must be in [0,1]");
+        thr[g] = e <= 0.0 ? 0 : (e >= 1.0 ? (1ull << 32) : (u64)(e * 4294967296.0));
+    }
+    std::vector<int32_t> known;
+    const bool doped = cfg->n_doped > 0 || cfg->n_soft > 0;
+    if (doped && (rc = build_known(d, cfg->doped_pos_host, cfg->n_doped, cfg->soft_pos_host, cfg->soft_count_host, cfg->n_soft, &known))) return rc;
+    CU(cudaMemcpyAsync(const_cast<u64 *>(p.thr), thr.data(), sizeof(u64) * thr.size(), cudaMemcpyHostToDevice, st));
+    if (doped) CU(cudaMemcpyAsync(const_cast<int32_t *>(p.known), known.data(), sizeof(int32_t) * d->L, cudaMemcpyHostToDevice, st));
+    else p.known = nullptr;
+    CU(cudaStreamSynchronize(st));               // host vectors leave scope at return; keep it simple
+    // state: Lij = 1 (tail CNs of a truncated code are never swept), everything else 0; no lane holds a frame yet
+    const size_t ch = p.chunks;
+    CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
+    CU(cudaMemsetAsync(p.v2c, 0, sizeof(u128) * (size_t)p.G * (p.E + 1) * ch, st));
+    CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+    CU(cudaMemsetAsync(p.y, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+    {
+        BpParams q = p;                          // control words, counters, position lists ("every position")
+        bp_launch_init_ctrl_only(q, d->n_frames, st);
+    }
+    bp_launch_wave_init(p, st);
+    bp_launch_stream_init(p, d->n_frames, st);
+    bp_launch_stream_harvest(p, 0, st);          // arms the first frames
+    CU(cudaGetLastError());
+    int *hf = nullptr;
+    if ((rc = host_flag(&hf))) return rc;
+    static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[0]) {
+        CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    }
+    const int H = cfg->harvest_every > 0 ? cfg->harvest_every : 16;
+    long long it = 0;
+    int nchunk = 0;
+    bool pending[2] = {false, false};
+    for (;;) {
+        for (int q = 0; q < H; q++, it++) {
+            p.iter = (int)(it & 0x3fffffff);
+            if (bp_launch_stream_iteration(d->dv, d->dc, p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+        }
+        bp_launch_count_pairs(d->dv, d->dc, p, st);
+        bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
+        CU(cudaGetLastError());
+        const int slot = nchunk & 1;
+        CU(cudaMemcpyAsync(hf + slot, p.alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ev[slot], st));
+        pending[slot] = true;
+        nchunk++;
+        const int prev = nchunk & 1;
+        if (pending[prev]) {
+            CU(cudaEventSynchronize(ev[prev]));
+            pending[prev] = false;
+            if (hf[prev] == 0) break;
+        }
+    }
+    if (iters_launched_host) *iters_launched_host = it;
     return 0;
 }
 
@@ -580,6 +710,39 @@ static void keep_pool_memory()
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+}
+
+// Host-buffer form of scldpc_bp_stream: graph tables come from host memory, per-frame results return to host memory
+// (int32 [G][frames_per_graph] each); the channel realisations are drawn on the device.
+extern "C" int scldpc_stream_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const scldpc_stream_cfg_t *cfg,
+                                  int32_t *iters_host, int32_t *residual_host, int32_t *blocks_err_host,
+                                  int32_t *erasures_exp_host, int32_t *blocks_err_exp_host, long long *iters_launched_host)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!vn_cn_host || !cfg) return fail(SCLDPC_EINVAL, "NULL input pointer");
+    if ((rc = have_device())) return rc;
+    keep_pool_memory();
+    const size_t G = d->n_graphs, B = cfg->frames_per_graph > 0 ? cfg->frames_per_graph : 0;
+    const size_t n = (size_t)d->L * d->vns_pos, nk = (size_t)(d->L + d->dv - 1) * d->cns_pos, E = n * d->dv;
+    DevBuf vn_cn, vn_slot, cn_edge, scratch, ws, res;
+    const size_t ws_bytes = scldpc_bp_stream_workspace_bytes(d);
+    if (vn_cn.alloc(4 * G * E) || vn_slot.alloc(4 * G * E) || cn_edge.alloc(4 * G * nk * d->dc) || scratch.alloc(4 * G * nk) ||
+        ws.alloc(ws_bytes) || res.alloc(4 * 5 * G * B))
+        return fail(SCLDPC_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStream_t st = nullptr;
+    CU(cudaMemcpyAsync(vn_cn.p, vn_cn_host, 4 * G * E, cudaMemcpyHostToDevice, st));
+    scldpc_batch_t b{static_cast<int32_t *>(vn_cn.p), static_cast<int32_t *>(vn_slot.p), static_cast<int32_t *>(cn_edge.p), nullptr};
+    if ((rc = scldpc_graph_build_tables(d, &b, static_cast<int32_t *>(scratch.p), st))) return rc;
+    int32_t *r = static_cast<int32_t *>(res.p);
+    CU(cudaMemsetAsync(r, 0, 4 * 5 * G * B, st));
+    scldpc_stream_out_t out{r, r + G * B, r + 2 * G * B, r + 3 * G * B, r + 4 * G * B};
+    if ((rc = scldpc_bp_stream(d, &b, cfg, &out, ws.p, ws_bytes, iters_launched_host, st))) return rc;
+    int32_t *dsts[5] = {iters_host, residual_host, blocks_err_host, erasures_exp_host, blocks_err_exp_host};
+    for (int a = 0; a < 5; a++)
+        if (dsts[a]) CU(cudaMemcpyAsync(dsts[a], r + a * G * B, 4 * G * B, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
 }
 
 extern "C" int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const uint8_t *erased_host, int W, int max_it,

@@ -56,6 +56,33 @@ __device__ __forceinline__ void sparse_count(int *cnt, int base, u128 m)
     while (a) { int b = __ffsll((long long)a) - 1; atomicAdd(&cnt[base + 64 + b], 1); a &= a - 1; }
 }
 
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based: every (graph, position, socket) / (graph, frame, VN) has its own
+// number regardless of how work is split over threads, batches or GPUs.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// channel draw of (graph gid, frame f, VN v): erased iff the returned 32-bit number is below eps * 2^32
+__host__ __device__ __forceinline__ uint32_t channel_draw(uint64_t seed, uint64_t gid, uint32_t frame, uint32_t v)
+{
+    uint32_t r[4];
+    philox4x32_10(v, frame >> 2, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed ^ 0x6368616Eu, (uint32_t)(seed >> 32), r);
+    return r[frame & 3];
+}
+
 // one adjacency row (dc CN edges / dv VN slots) with the widest aligned loads the degree allows
 template <int D>
 __device__ __forceinline__ void load_row(const int32_t *row, int (&e)[D])
@@ -113,6 +140,18 @@ struct BpParams {
     int *n_list;              // [G][2] lengths of cn_list / vn_list
     int cn_pos_lim;           // CN positions that are ever swept (L+dv-1 terminated, L truncated)
     long long *swept;         // [G][2] CN / VN positions swept, summed over iterations (instrumentation)
+    const u64 *lane_mask;     // [G][W] finalisation kernels only look at these lanes (NULL: all lanes)
+    // frame streams (lane recycling): a finished frame frees its bit lane for the next channel realisation
+    u64 *arm_mask;            // [G][W] lanes that take a new frame in the next VN sweep
+    u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested
+    int *lane_frame;          // [G][lanes] frame id decoded in the lane, -1 if idle
+    int *lane_iter;           // [G][lanes] iterations executed by the lane's current frame
+    int *next_frame;          // [G] next frame id of the graph's stream
+    const u64 *thr;           // [G] erasure threshold eps * 2^32 of the graph's channel
+    const int32_t *known;     // [L] doping: the first known[pos] VNs of a position are known (NULL: none)
+    int frames_per_graph;     // stream length B
+    uint64_t seed, first_graph;
+    int *s_iters, *s_residual, *s_blocks_err, *s_erasures_exp, *s_blocks_err_exp;   // [G][B] per-frame results
     // outputs
     int *iters;               // [G][lanes]
     int *rows;                // [G][max_rows][lanes][3]

@@ -10,27 +10,6 @@
 namespace scldpc {
 
 // ------------------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al., SC'11) -- counter-based, so every (graph, position, socket) / (graph, frame, VN)
-// has its own number regardless of how work is split over threads, batches or GPUs.
-// ------------------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                       uint32_t k0, uint32_t k1, uint32_t (&out)[4])
-{
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n1 = (uint32_t)p1;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        const uint32_t n3 = (uint32_t)p0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += W0; k1 += W1;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // CN tables
 // ------------------------------------------------------------------------------------------------------------
 __global__ void graph_fill_kernel(const int32_t *vn_cn, int32_t *cn_edge, int32_t *fill, int n, int nk, int dv, int dc,
@@ -209,10 +188,10 @@ size_t graph_generate_scratch_words(int G, int L, int cns_pos, int dv, int dc, i
 // ------------------------------------------------------------------------------------------------------------
 // channel
 // ------------------------------------------------------------------------------------------------------------
-// chan[g][v][w] bit b = 1 (erased) iff u32(seed; graph, frame 64w+b, v) < eps * 2^32, unless v is among the first
+// chan[g][v][w] bit b = 1 (erased) iff channel_draw(seed; graph, frame first_frame+64w+b, v) < eps * 2^32, unless v is among the first
 // known[pos] VNs of its position (doping).  One Philox call yields the draws of 4 consecutive frames.
 __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, int vns_pos, const int32_t *known,
-                                        u64 thr, uint64_t seed, uint64_t first_graph)
+                                        u64 thr, uint64_t seed, uint64_t first_graph, uint32_t first_frame)
 {
     const int g = blockIdx.y;
     const uint64_t gid = first_graph + (uint64_t)g;
@@ -225,7 +204,8 @@ __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, i
 #pragma unroll 4
             for (int q = 0; q < 16; q++) {
                 uint32_t r[4];
-                philox4x32_10((uint32_t)v, (uint32_t)(w * 16 + q), (uint32_t)gid, (uint32_t)(gid >> 32),
+                // frame ids of this Philox call: first_frame + 64w + 4q + {0,1,2,3}; first_frame is a multiple of 4
+                philox4x32_10((uint32_t)v, (first_frame >> 2) + (uint32_t)(w * 16 + q), (uint32_t)gid, (uint32_t)(gid >> 32),
                               (uint32_t)seed ^ 0x6368616Eu, (uint32_t)(seed >> 32), r);
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
@@ -239,7 +219,7 @@ __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, i
 }
 
 void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
-                      uint64_t seed, uint64_t first_graph, cudaStream_t st)
+                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st)
 {
     u64 thr;
     if (eps <= 0.0) thr = 0;
@@ -247,7 +227,7 @@ void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos,
     else thr = (u64)(eps * 4294967296.0);
     const long long items = (long long)n * W;
     unsigned bx = (unsigned)((items + 255) / 256 < 2368 ? (items + 255) / 256 : 2368);
-    channel_generate_kernel<<<dim3(bx, G), 256, 0, st>>>(chan, n, W, n_frames, vns_pos, known_dev, thr, seed, first_graph);
+    channel_generate_kernel<<<dim3(bx, G), 256, 0, st>>>(chan, n, W, n_frames, vns_pos, known_dev, thr, seed, first_graph, first_frame);
 }
 
 // bytes [G][F][n] (1 = erased) -> bit-sliced words [G][n][W]

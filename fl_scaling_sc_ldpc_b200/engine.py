@@ -121,10 +121,11 @@ class FrameBatch:
                                                        ctypes.c_void_p(self.chan.data_ptr()), _stream()))
         return self
 
-    def generate_erasures(self, eps, seed: int, first_graph_id: int = 0, doping_points=()) -> "FrameBatch":
+    def generate_erasures(self, eps, seed: int, first_graph_id: int = 0, doping_points=(), first_frame: int = 0) -> "FrameBatch":
         """BEC(eps) realisations on the device; ``eps`` is a float or one value per graph of the batch.
         ``doping_points``: list of positions (hard doping) or dict {position: alpha} (soft doping: the first
-        int(alpha*M) VNs are known, PD.py:175-183)."""
+        int(alpha*M) VNs are known, PD.py:175-183).  Lane f holds frame ``first_frame + f`` of the graph's channel
+        stream (``first_frame`` a multiple of 4)."""
         hard, soft_p, soft_c = [], [], []
         if isinstance(doping_points, dict):
             for pos, alpha in doping_points.items():
@@ -145,7 +146,8 @@ class FrameBatch:
         for dims, ptr, ep, gid in calls:
             _lib.check(L.scldpc_channel_generate(
                 ctypes.byref(dims), ctypes.c_void_p(ptr), ctypes.c_double(ep), arr(hard), len(hard),
-                arr(soft_p), arr(soft_c), len(soft_p), ctypes.c_uint64(seed), ctypes.c_uint64(gid), _stream()))
+                arr(soft_p), arr(soft_c), len(soft_p), ctypes.c_uint64(seed), ctypes.c_uint64(gid), ctypes.c_uint32(first_frame),
+                _stream()))
         return self
 
     def erasures_host(self) -> np.ndarray:
@@ -247,6 +249,58 @@ def decode_bp_window(fb: FrameBatch, W: int, max_it: int, init_it: int = 0, squa
     if not collect:
         return res, erased, rows, 0
     return _collect(fb, res, erased, rows, edge_updates=work.value)
+
+
+@dataclass
+class StreamResult:
+    """Per-frame outputs of ``decode_bp_stream``; arrays are [n_graphs][frames_per_graph], indexed by frame id."""
+    iters: np.ndarray
+    residual: np.ndarray
+    blocks_err: np.ndarray
+    erasures_exp: np.ndarray
+    blocks_err_exp: np.ndarray
+    iters_launched: int = 0
+    edge_updates: int = 0
+
+
+def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, first_graph_id: int = 0, is_term: bool = True,
+                     doping_points=(), harvest_every: int = 16, exp_all: bool = False, collect: bool = True):
+    """Unlimited-iteration full BP over a stream of ``frames_per_graph`` frames per graph with lane recycling
+    (``scldpc_bp_stream``).  Frame f of graph g is the channel realisation ``generate_erasures(..., first_frame=...)``
+    puts in lane f - first_frame; the graphs are the ones resident in ``fb`` (``fb.n_frames`` lanes are used)."""
+    L = _lib.lib()
+    G, B = fb.n_graphs, int(frames_per_graph)
+    eps_arr = np.full(G, float(eps)) if np.ndim(eps) == 0 else np.asarray(eps, np.float64)
+    assert eps_arr.shape == (G,)
+    hard, soft_p, soft_c = [], [], []
+    if isinstance(doping_points, dict):
+        for pos, alpha in doping_points.items():
+            soft_p.append(int(pos)); soft_c.append(int(alpha * fb.ens.M))
+    else:
+        hard = [int(p) for p in doping_points]
+    arr = lambda xs: np.asarray(xs or [0], np.int32)
+    a_h, a_sp, a_sc = arr(hard), arr(soft_p), arr(soft_c)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p).value
+    flags = (F_TERMINATED if is_term else 0) | (F_EXP_ALL if exp_all else 0)
+    cfg = _lib.StreamCfg(B, int(harvest_every), flags, len(hard), len(soft_p), ptr(eps_arr), ptr(a_h), ptr(a_sp), ptr(a_sc),
+                         int(seed), int(first_graph_id))
+    res = torch.zeros((5, G, B), dtype=torch.int32, device=fb.device)
+    out = _lib.StreamOut(*[res[i].data_ptr() for i in range(5)])
+    need = L.scldpc_bp_stream_workspace_bytes(ctypes.byref(fb.dims))
+    if need == 0:
+        raise _lib.ScldpcError(L.scldpc_last_error().decode())
+    if fb._ws is None or fb._ws.numel() < need:
+        fb._ws = None
+        fb._ws = torch.empty(need, dtype=torch.uint8, device=fb.device)
+    launched = ctypes.c_longlong(0)
+    _lib.check(L.scldpc_bp_stream(ctypes.byref(fb.dims), ctypes.byref(fb.cbatch), ctypes.byref(cfg), ctypes.byref(out),
+                                  ctypes.c_void_p(fb._ws.data_ptr()), ctypes.c_size_t(fb._ws.numel()), ctypes.byref(launched),
+                                  _stream()))
+    if not collect:
+        return res, launched.value
+    r = res.cpu().numpy()
+    return StreamResult(r[0], r[1], r[2], r[3], r[4], iters_launched=launched.value,
+                        edge_updates=int(r[0].astype(np.int64).sum()) * 2 * fb.ens.E)
 
 
 def decode_host(ens: Ensemble, vn_cn: np.ndarray, erased: np.ndarray, W: int = 0, max_it: int = UNLIMITED, init_it: int = 0,

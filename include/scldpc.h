@@ -44,6 +44,7 @@ extern "C" {
 #define SCLDPC_F_TRAJECTORY 2u   /* record (deg_1_iter, dVNs, first erased position) per iteration              */
 #define SCLDPC_F_SQUARE 4u       /* window decoder: square window (BP_SW.c) instead of classical (BP_FULL.c)    */
 #define SCLDPC_F_EXP_ALL 8u      /* expurgated statistics over all positions (decodeBP_SW) instead of the first */
+#define SCLDPC_F_STREAM 32u      /* internal: workspace sizing of scldpc_bp_stream */
 #define SCLDPC_F_CHAN_PACKED 16u /* scldpc_decode_host: erased_host is already bit-sliced, uint64 [G][n][n_words] */
 
 typedef struct {
@@ -97,12 +98,12 @@ int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *
 size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting);
 
 /* ---- channel ------------------------------------------------------------------------------------------ */
-/* BEC realisations, bit-sliced (channel_doped, BP_FULL.c:1547-1574; PD.py:154, :174-192).  Frame f of graph g
- * uses Philox stream (seed, first_graph_id+g, f).  Hard doping: all VNs of positions doped_pos_host[] known.
+/* BEC realisations, bit-sliced (channel_doped, BP_FULL.c:1547-1574; PD.py:154, :174-192).  Lane f of graph g holds
+ * frame first_frame_id+f (a multiple of 4) of Philox stream (seed, first_graph_id+g).  Hard doping: all VNs of positions doped_pos_host[] known.
  * Soft doping: the first soft_count_host[p] VNs of position soft_pos_host[p] known (int(alpha*M), PD.py:177). */
 int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
                             int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
-                            uint64_t seed, uint64_t first_graph_id, void *stream);
+                            uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, void *stream);
 
 /* Packs byte-per-VN erasure patterns (host, [G][n_frames][n], 1 = erased) into chan_dev. */
 int scldpc_channel_pack_host(const scldpc_dims_t *d, const uint8_t *erased_host, uint64_t *chan_dev, void *stream);
@@ -116,6 +117,34 @@ size_t scldpc_bp_workspace_bytes(const scldpc_dims_t *d, uint32_t flags);
 int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
                    const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                    int *iters_launched_host, void *stream);
+
+/* Frame streams (lane recycling).  Each graph of the batch decodes frames 0 .. frames_per_graph-1 of its channel
+ * stream (the same realisations scldpc_channel_generate produces for those frame ids) with unlimited-iteration full
+ * BP; d->n_frames lanes per graph are used, and a lane whose frame has stopped is harvested and re-armed with the next
+ * frame id, so stragglers do not hold the other lanes of their word idle.  Results are indexed by frame id,
+ * int32 [G][frames_per_graph].  b->chan_dev is not used. */
+typedef struct {
+    int32_t frames_per_graph;        /* stream length per graph                                                */
+    int32_t harvest_every;           /* iterations between harvests (<= 0: 16)                                 */
+    uint32_t flags;                  /* SCLDPC_F_TERMINATED, SCLDPC_F_EXP_ALL                                  */
+    int32_t n_doped, n_soft;
+    const double *eps_host;          /* [G] erasure probability of each graph's channel                        */
+    const int32_t *doped_pos_host, *soft_pos_host, *soft_count_host;   /* doping as in scldpc_channel_generate  */
+    uint64_t seed, first_graph_id;
+} scldpc_stream_cfg_t;
+typedef struct {
+    int32_t *iters_dev, *residual_dev, *blocks_err_dev, *erasures_exp_dev, *blocks_err_exp_dev;
+} scldpc_stream_out_t;
+size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d);
+int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b, const scldpc_stream_cfg_t *cfg,
+                     const scldpc_stream_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                     long long *iters_launched_host, void *stream);
+
+/* scldpc_bp_stream with HOST buffers: graph tables vn_cn_host [G][n][dv] in, per-frame results int32
+ * [G][frames_per_graph] out (any may be NULL); channel realisations are drawn on the device. */
+int scldpc_stream_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const scldpc_stream_cfg_t *cfg,
+                       int32_t *iters_host, int32_t *residual_host, int32_t *blocks_err_host, int32_t *erasures_exp_host,
+                       int32_t *blocks_err_exp_host, long long *iters_launched_host);
 
 /* Sliding-window BP -- decodeBP_SW (square: BP_SW.c:628-912; classical: BP_FULL.c:627-897).  init_it <= 0 means
  * max_it (BP_SW.c:2099-2102).  Without SCLDPC_F_TERMINATED the CN window is clipped at L*cns_pos (derived

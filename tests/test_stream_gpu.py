@@ -1,0 +1,67 @@
+"""Frame streams (lane recycling): every frame id must decode exactly as in a synchronous batch of the same channel
+realisations -- iterations, residual, block and expurgated statistics -- whatever lane it happened to land in."""
+import numpy as np
+import pytest
+
+import fl_scaling_sc_ldpc_b200 as eng
+
+pytestmark = pytest.mark.gpu
+KEYS = ("iters", "residual", "blocks_err", "erasures_exp", "blocks_err_exp")
+
+
+def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
+    """frames 0..B-1 decoded 128 at a time with the synchronous decoder on the same graphs"""
+    G = fb_graphs.n_graphs
+    out = {k: np.zeros((G, B), np.int32) for k in KEYS}
+    for f0 in range(0, B, 128):
+        k = min(128, B - f0)
+        fb = eng.FrameBatch(ens, G, k, 2)
+        fb.vn_cn.copy_(fb_graphs.vn_cn); fb._build_tables()
+        fb.generate_erasures(eps, seed, first_graph_id=3, doping_points=doping, first_frame=f0)
+        r = eng.decode_bp_full(fb, 0, is_term)
+        for key in KEYS:
+            out[key][:, f0:f0 + k] = getattr(r, key)
+    return out
+
+
+@pytest.mark.parametrize("L,M,lanes,B,eps", [(10, 50, 128, 700, [0.44, 0.50]), (16, 64, 100, 333, [0.47, 0.41]), (8, 32, 256, 256, [0.5, 0.3])])
+def test_stream_equals_synchronous_batches(L, M, lanes, B, eps):
+    ens = eng.Ensemble(4, 8, L, M)
+    fbg = eng.FrameBatch(ens, 2, lanes).generate_graphs(21, first_graph_id=3)
+    for is_term in (True, False):
+        ref = sync_reference(fbg, ens, B, eps, 55, is_term)
+        for H in (1, 7, 16):
+            s = eng.decode_bp_stream(fbg, B, eps, 55, first_graph_id=3, is_term=is_term, harvest_every=H)
+            for key in KEYS:
+                assert (getattr(s, key) == ref[key]).all(), (is_term, H, key)
+            assert s.iters_launched >= ref["iters"].max()
+
+
+def test_stream_with_doping_and_other_degrees():
+    ens = eng.Ensemble(3, 6, 12, 48)
+    fbg = eng.FrameBatch(ens, 1, 128).generate_graphs(5, first_graph_id=3)
+    ref = sync_reference(fbg, ens, 400, 0.42, 9, True, doping=[5])
+    s = eng.decode_bp_stream(fbg, 400, 0.42, 9, first_graph_id=3, doping_points=[5])
+    for key in KEYS:
+        assert (getattr(s, key) == ref[key]).all(), key
+    ref = sync_reference(fbg, ens, 130, 0.45, 9, True, doping={2: 0.5})
+    s = eng.decode_bp_stream(fbg, 130, 0.45, 9, first_graph_id=3, doping_points={2: 0.5})
+    for key in KEYS:
+        assert (getattr(s, key) == ref[key]).all(), key
+
+
+def test_stream_full_size_sample():
+    """(4,8), L=50, M=10000, eps=0.47: a 256-lane stream of 384 frames against synchronous decoding of the same frames"""
+    ens = eng.Ensemble(4, 8, 50, 10000)
+    fbg = eng.FrameBatch(ens, 1, 256, 4).generate_graphs(77, first_graph_id=3)
+    s = eng.decode_bp_stream(fbg, 384, 0.47, 78, first_graph_id=3)
+    out = {k: [] for k in KEYS}
+    for f0 in (0, 128, 256):
+        fb = eng.FrameBatch(ens, 1, 128, 2)
+        fb.vn_cn.copy_(fbg.vn_cn); fb._build_tables()
+        fb.generate_erasures(0.47, 78, first_graph_id=3, first_frame=f0)
+        r = eng.decode_bp_full(fb, 0, True)
+        for k in KEYS:
+            out[k].append(getattr(r, k))
+    for k in KEYS:
+        assert (getattr(s, k) == np.concatenate(out[k], axis=1)).all(), k
