@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...   the reference's CPU decoder on the host cores
 
 A *step* decodes 4 graph realisations (one per eps of the 0.46..0.49 sweep of BASELINE config 2) x B frames each
-(default B = 4096, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
+(default B = 8192, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
 or finished.  Default mode "stream": a lane whose frame has stopped is re-armed with the graph's next channel
 realisation (scldpc_bp_stream); mode "batch": B = lanes, every lane decodes one frame (scldpc_bp_full).  Throughput counts USEFUL
 work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same formula as for the CPU
@@ -39,7 +39,7 @@ E_EDGES = L * M * DV
 N_VNS = L * M
 WORKLOAD = ("full BP unlimited iterations, (4,8) SC-LDPC terminated L=50 M=10000, BEC eps sweep "
             "{0.46,0.47,0.48,0.49}: 4 graphs x B frames per step")
-FRAMES_PER_STREAM = 4096
+FRAMES_PER_STREAM = 8192
 CAP_LO = 2   # reference arm: iterations of the shorter of the two capped runs
 METRIC = "edge-updates/s (frames/s alongside), (4,8) SC-LDPC L=50 M=10000 BEC BP"
 

@@ -365,13 +365,21 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
                 // new frames: Lji = channel value on every edge (BP_FULL.c:913-917), previous decision "all erased"
                 const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
                 u128 cw = zero128();
+                // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
+                // usually shared by up to four armed lanes
+                uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
                 for (int half = 0; half < 2; half++) {
                     u64 m = half ? arm.y : arm.x, w = 0;
-                    while (m) {
+                    while (m && !forced) {
                         const int b = __ffsll((long long)m) - 1;
                         m &= m - 1;
-                        const int fr = p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
-                        if (!forced && (u64)channel_draw(p.seed, gid, (uint32_t)fr, (uint32_t)v) < thr) w |= 1ull << b;
+                        const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
+                        if ((fr >> 2) != blk) {
+                            blk = fr >> 2;
+                            philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
+                                          (uint32_t)(p.seed >> 32), r4);
+                        }
+                        if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
                     }
                     if (half) cw.y = w; else cw.x = w;
                 }
