@@ -34,6 +34,7 @@ void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int 
 void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
 void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
 int peel_grid(int total_size, long long total_frames);
+size_t peel_state_words(int n_cn_all, int total_size);
 int peel_launch(PeelParams p, int grid, cudaStream_t st);
 void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
                           long long *counts, cudaStream_t st);
@@ -72,6 +73,7 @@ static int check_dims(const scldpc_dims_t *d)
     const int W = d->n_words;
     if (W < 2 || W > SCLDPC_MAX_WORDS || (W & (W - 1))) return fail(SCLDPC_EINVAL, "n_words must be 2, 4, 8 or 16");
     if (d->n_frames < 0 || d->n_frames > 64 * W) return fail(SCLDPC_EINVAL, "n_frames out of range");
+    if (d->n_graphs > 65535) return fail(SCLDPC_EINVAL, "at most 65535 graphs per batch");
     if ((long long)d->L * d->vns_pos * d->dv >= INT_MAX / 2) return fail(SCLDPC_EINVAL, "graph too large for int32 edge ids");
     return 0;
 }
@@ -582,7 +584,7 @@ extern "C" size_t scldpc_peel_workspace_bytes(const scldpc_dims_t *d, int n_cn_a
     if (check_dims(d) || have_device()) return 0;
     const int grid = peel_grid(total_size, (long long)d->n_graphs * d->n_frames);
     if (grid < 0) { fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap"); return 0; }
-    return sizeof(u64) * (size_t)grid * (size_t)n_cn_all;
+    return sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size);
 }
 
 extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *vn_cn_dev, const uint64_t *chan_dev, int n_cn_all,
@@ -599,7 +601,7 @@ extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *v
     if (frames == 0) return 0;
     const int grid = peel_grid(total_size, frames);
     if (grid < 0) return fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap");
-    if (workspace_bytes < sizeof(u64) * (size_t)grid * (size_t)n_cn_all) return fail(SCLDPC_ENOMEM, "workspace too small");
+    if (workspace_bytes < sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size)) return fail(SCLDPC_ENOMEM, "workspace too small");
     PeelParams p;
     memset(&p, 0, sizeof p);
     p.n = d->L * d->vns_pos; p.dv = d->dv; p.n_cn_all = n_cn_all; p.total_size = total_size; p.num_steps = num_steps;

@@ -177,6 +177,7 @@ struct BpFinalOut {
 struct PeelParams {
     int n, dv, n_cn_all, total_size, num_steps, W, n_frames, G;
     int n_words1, n_l1, n_l2;      // bitmap words, level-1 entries (1024 CNs each), level-2 entries (32768 CNs each)
+    int bits_global;               // 1: the bitmap lives in global memory behind the block's CN state
     const int32_t *vn_cn;          // [G][n][dv]
     const u64 *chan;               // [G][n][W]
     u64 *state;                    // [gridDim.x][n_cn_all]  (degree << 32) + id sum

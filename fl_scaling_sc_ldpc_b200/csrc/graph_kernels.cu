@@ -68,10 +68,10 @@ int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge,
 // keys[seg][s] = (random << KEY_IDX_BITS) | s for s < S, all-ones padding up to Spad.  seg = g*npos + pos.
 __global__ void graph_keys_kernel(u64 *keys, int S, int Spad, int npos, uint64_t seed, uint64_t first_graph)
 {
-    const int seg = blockIdx.y;
+    const int seg = blockIdx.x;                       // segments on grid.x: G * npos can exceed the 65535 limit of grid.y
     const uint64_t gid = first_graph + (uint64_t)(seg / npos);
     const uint32_t pos = (uint32_t)(seg % npos);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Spad / 2; q += gridDim.x * blockDim.x) {
+    for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < Spad / 2; q += gridDim.y * blockDim.x) {
         uint32_t r[4];
         // counter = (socket pair, position, graph id); key = seed ^ domain tag "graph"
         philox4x32_10((uint32_t)q, pos, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)seed ^ 0x67726170u,
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(SORT_THREADS) bitonic_tile_kernel(u64 *keys, i
 {
     __shared__ u64 s[SORT_TILE];
     const int tile = Spad < SORT_TILE ? Spad : SORT_TILE;
-    const size_t base = (size_t)blockIdx.y * Spad + (size_t)blockIdx.x * tile;
+    const size_t base = (size_t)blockIdx.x * Spad + (size_t)blockIdx.y * tile;
     for (int i = threadIdx.x; i < tile; i += SORT_THREADS) s[i] = keys[base + i];
     __syncthreads();
     int lt = 0;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(SORT_THREADS) bitonic_tile_kernel(u64 *keys, i
             for (int t = threadIdx.x; t < tile / 2; t += SORT_THREADS) {
                 const int lo = ((t >> j) << (j + 1)) | (t & ((1 << j) - 1));
                 const int hi = lo | (1 << j);
-                const size_t gi = (size_t)blockIdx.x * tile + lo;      // index inside the segment
+                const size_t gi = (size_t)blockIdx.y * tile + lo;      // index inside the segment
                 const bool up = ((gi >> k) & 1) == 0;
                 cmpx(s[lo], s[hi], up);
             }
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(SORT_THREADS) bitonic_tile_kernel(u64 *keys, i
 // one global compare-exchange pass (distance 2^j >= SORT_TILE) of stage k
 __global__ void bitonic_global_kernel(u64 *keys, int Spad, int k, int j)
 {
-    u64 *seg = keys + (size_t)blockIdx.y * Spad;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Spad / 2; t += gridDim.x * blockDim.x) {
+    u64 *seg = keys + (size_t)blockIdx.x * Spad;
+    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < Spad / 2; t += gridDim.y * blockDim.x) {
         const int lo = ((t >> j) << (j + 1)) | (t & ((1 << j) - 1));
         const int hi = lo | (1 << j);
         const bool up = ((lo >> k) & 1) == 0;
@@ -160,15 +160,15 @@ int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns
     const int segs = G * npos;
     unsigned bx = (unsigned)((Spad / 2 + 255) / 256);
     if (bx > 64) bx = 64;
-    graph_keys_kernel<<<dim3(bx, segs), 256, 0, st>>>(keys, S, Spad, npos, seed, first_graph);
+    graph_keys_kernel<<<dim3(segs, bx), 256, 0, st>>>(keys, S, Spad, npos, seed, first_graph);
     const int tile = Spad < SORT_TILE ? Spad : SORT_TILE;
     int lt = 0;
     while ((1 << lt) < tile) lt++;
-    const dim3 gt(Spad / tile, segs);
+    const dim3 gt(segs, Spad / tile);
     // stages 1..lt entirely inside a tile
     bitonic_tile_kernel<<<gt, SORT_THREADS, 0, st>>>(keys, Spad, 1, lt);
     for (int k = lt + 1; k <= lg; k++) {
-        for (int j = k - 1; j >= lt; j--) bitonic_global_kernel<<<dim3(bx, segs), 256, 0, st>>>(keys, Spad, k, j);
+        for (int j = k - 1; j >= lt; j--) bitonic_global_kernel<<<dim3(segs, bx), 256, 0, st>>>(keys, Spad, k, j);
         bitonic_tile_kernel<<<gt, SORT_THREADS, 0, st>>>(keys, Spad, k, k);
     }
     const long long E = (long long)L * vns_pos * dv;

@@ -13,6 +13,8 @@
 //     being degree one.
 // The random pick of step s of frame f is k = philox4x32_10(counter = (s/4, 0, f.lo, f.hi), key = seed)[s%4] mod
 // (number of degree-one CNs); the oracle is fed the same 32-bit draws, so trajectories are compared bit for bit.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scldpc {
@@ -54,15 +56,19 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-// one warp per block; dynamic shared memory: bitmap words | level-1 counts | level-2 counts
+// one warp per block; dynamic shared memory: [bitmap words |] level-1 counts | level-2 counts.  When the bitmap does not
+// fit next to the counts (M = 1e5: 2.5e6 CNs = 312 KB) it lives in global memory behind the block's CN state (it is
+// touched by a handful of words per step and stays L2-resident); the counts always stay in shared memory.
 __global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
 {
     extern __shared__ unsigned s_mem[];
-    unsigned *bits = s_mem;
-    int *l1 = reinterpret_cast<int *>(s_mem + p.n_words1);
-    int *l2 = l1 + p.n_l1;
     const int lane = threadIdx.x;
-    u64 *st = p.state + (size_t)blockIdx.x * p.n_cn_all;
+    const size_t st_words = (size_t)p.n_cn_all + (p.bits_global ? ((size_t)p.n_words1 + 1) / 2 : 0);   // u64 per block
+    u64 *st = p.state + (size_t)blockIdx.x * st_words;
+    unsigned *bits = p.bits_global ? reinterpret_cast<unsigned *>(st + p.n_cn_all) : s_mem;
+    int *l1 = reinterpret_cast<int *>(s_mem + (p.bits_global ? 0 : p.n_words1));
+    int *l2 = l1 + p.n_l1;
+    const int l2q = (p.n_l2 + 31) / 32;                           // level-2 entries per lane
     const long long total_frames = (long long)p.G * p.n_frames;
 
     for (long long fr = blockIdx.x; fr < total_frames; fr += gridDim.x) {
@@ -72,7 +78,8 @@ __global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
         const int fb = f & 63;
         // ---- residual graph of the erased VNs (schedule, PD.py:750-757) ----
         for (int i = lane; i < p.n_cn_all; i += 32) st[i] = 0;
-        for (int i = lane; i < p.n_words1 + p.n_l1 + p.n_l2; i += 32) s_mem[i] = 0;
+        for (int i = lane; i < p.n_words1; i += 32) bits[i] = 0;
+        for (int i = lane; i < p.n_l1 + p.n_l2; i += 32) l1[i] = 0;
         __syncwarp();
         int n_er = 0;
         for (int v0 = 0; v0 < p.n; v0 += 32) {
@@ -115,12 +122,19 @@ __global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
                             (uint32_t)(p.seed >> 32), rnd);
             int k = (int)(rnd[step & 3] % (uint32_t)cnt1);
             // ---- select the k-th set bit ----
-            int a = lane < p.n_l2 ? l2[lane] : 0;
+            int a = 0;
+            for (int q = 0; q < l2q; q++) a += (lane * l2q + q) < p.n_l2 ? l2[lane * l2q + q] : 0;
             int inc = warp_incl_scan(a, lane);
             unsigned bal = __ballot_sync(0xffffffffu, k < inc);
             int sel = __ffs(bal) - 1;
             k -= __shfl_sync(0xffffffffu, inc - a, sel);
-            const int b2 = sel;
+            int b2 = sel * l2q;
+            for (int q = 0; q + 1 < l2q; q++) {                    // at most a few entries inside the selected lane
+                const int c2 = l2[b2];
+                if (k < c2) break;
+                k -= c2;
+                b2++;
+            }
             a = (b2 * 32 + lane) < p.n_l1 ? l1[b2 * 32 + lane] : 0;
             inc = warp_incl_scan(a, lane);
             bal = __ballot_sync(0xffffffffu, k < inc);
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
             k -= __shfl_sync(0xffffffffu, inc - a, sel);
             const int b1 = b2 * 32 + sel;
             const int wi = b1 * 32 + lane;
-            const unsigned word = wi < p.n_words1 ? bits[wi] : 0u;
+            const unsigned word = wi < p.n_words1 ? (p.bits_global ? __ldcg(bits + wi) : bits[wi]) : 0u;
             a = __popc(word);
             inc = warp_incl_scan(a, lane);
             bal = __ballot_sync(0xffffffffu, k < inc);
@@ -197,13 +211,26 @@ __global__ void peel_variance_kernel(const int32_t *r1, int n_frames, int row_le
     counts[s] += cnt;
 }
 
-size_t peel_smem_bytes(int total_size, int *n_words1, int *n_l1, int *n_l2)
+// shared memory per block; *bits_global = 1 when the bitmap has to live in global memory
+size_t peel_smem_bytes(int total_size, int *n_words1, int *n_l1, int *n_l2, int *bits_global)
 {
     const int w = (total_size + 31) / 32, a = (w + 31) / 32, b = (a + 31) / 32;
     if (n_words1) *n_words1 = w;
     if (n_l1) *n_l1 = a;
     if (n_l2) *n_l2 = b;
-    return sizeof(unsigned) * ((size_t)w + a + b);
+    size_t limit = 96 * 1024;                                                // keep >= 2 frames per SM in flight
+    if (const char *e = getenv("SCLDPC_PEEL_SMEM_LIMIT")) limit = (size_t)atol(e);   // tests force the global-bitmap path
+    const bool big = sizeof(unsigned) * ((size_t)w + a + b) > limit;
+    if (bits_global) *bits_global = big ? 1 : 0;
+    return sizeof(unsigned) * ((big ? 0 : (size_t)w) + a + b);
+}
+
+// u64 words of workspace per block
+size_t peel_state_words(int n_cn_all, int total_size)
+{
+    int w = 0, big = 0;
+    peel_smem_bytes(total_size, &w, nullptr, nullptr, &big);
+    return (size_t)n_cn_all + (big ? ((size_t)w + 1) / 2 : 0);
 }
 
 int peel_grid(int total_size, long long total_frames)
@@ -212,8 +239,9 @@ int peel_grid(int total_size, long long total_frames)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const size_t smem = peel_smem_bytes(total_size, nullptr, nullptr, nullptr);
-    if (smem > (size_t)max_smem) return -1;
+    int n_l2 = 0;
+    const size_t smem = peel_smem_bytes(total_size, nullptr, nullptr, &n_l2, nullptr);
+    if (smem > (size_t)max_smem || n_l2 > 32 * 8) return -1;
     long long per_sm = (long long)(max_smem) / (long long)(smem + 1024);
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
@@ -224,8 +252,8 @@ int peel_grid(int total_size, long long total_frames)
 
 int peel_launch(PeelParams p, int grid, cudaStream_t st)
 {
-    const size_t smem = peel_smem_bytes(p.total_size, &p.n_words1, &p.n_l1, &p.n_l2);
-    if (p.n_l2 > 32) return -1;                                  // more than 2^20 CNs: one more level would be needed
+    const size_t smem = peel_smem_bytes(p.total_size, &p.n_words1, &p.n_l1, &p.n_l2, &p.bits_global);
+    if (p.n_l2 > 32 * 8) return -1;                              // more than 2^23 CNs: one more level would be needed
     if (cudaFuncSetAttribute(peel_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
     g_prof.launches += 1;
     peel_trajectory_kernel<<<grid, 32, smem, st>>>(p);

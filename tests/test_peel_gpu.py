@@ -58,6 +58,14 @@ def test_peel_many_frames_per_graph_matches_oracle():
                 assert rec[g, f] == o_rec and ner[g, f] == er[g, f].sum()
 
 
+def test_peel_global_bitmap_path(monkeypatch):
+    """very large M keeps the degree-one bitmap in global memory; forced here on a small case"""
+    monkeypatch.setenv("SCLDPC_PEEL_SMEM_LIMIT", "64")
+    test_peel_trajectories_match_reference("t0")
+    test_peel_trajectories_match_reference("t1")
+    test_peel_many_frames_per_graph_matches_oracle()
+
+
 def test_variance_accumulation_matches_numpy():
     """calc_nu_chunk / calc_var_chunk (est_scaling_params.py:90-94,131-138) restated in NumPy vs the fused kernel"""
     rng = np.random.default_rng(3)
