@@ -43,8 +43,8 @@ __global__ void bp_wave_init_kernel(BpParams p)
 // ------------------------------------------------------------------------------------------------------------
 // check-node sweep over the listed positions
 // ------------------------------------------------------------------------------------------------------------
-template <int DC, bool TRAJ>
-__global__ void __launch_bounds__(256, TRAJ ? 3 : 5) bp_cn_wave_kernel(BpParams p)
+template <int DC, bool TRAJ, bool HEAD = false>
+__global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
@@ -80,6 +80,22 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 5) bp_cn_wave_kernel(BpParams 
             acc = zero128();
 #pragma unroll
             for (int j = DC - 1; j >= 0; j--) { out[j] |= acc; acc |= in[j]; }
+            if (HEAD && c < p.cn_dis_lim) {
+                // Unscanned head of simulate_sc_ldpc (is_bounded = False): a slot below the scan start is only decoded
+                // when a removal leaves it with one user (subtract_interference, PD.py:308-311), so a CN that starts with
+                // exactly one erased neighbour never resolves it: its outgoing messages stay erasures.
+                u128 *dp = p.cn_dis + ((size_t)g * p.cn_dis_lim + c) * ch + k;
+                u128 dis;
+                if (p.first_iter) {
+                    u128 one = zero128(), two = zero128();
+#pragma unroll
+                    for (int j = 0; j < DC; j++) { two |= one & in[j]; one |= in[j]; }
+                    dis = one & ~two;
+                    *dp = dis;
+                } else dis = *dp;
+#pragma unroll
+                for (int j = 0; j < DC; j++) out[j] |= dis;
+            }
             u128 *dst = c2v + ((size_t)c * DC) * ch + k;
 #pragma unroll
             for (int j = 0; j < DC; j++) dst[(size_t)j * ch] = out[j];
@@ -552,7 +568,8 @@ static void launch_wave_iteration(const BpParams &p, bool traj, cudaStream_t st,
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    if (traj) bp_cn_wave_kernel<DC, true><<<gc, block, 0, st>>>(p);
+    if (p.cn_dis_lim > 0) bp_cn_wave_kernel<DC, false, true><<<gc, block, 0, st>>>(p);     // error-rate runs only (no trajectory)
+    else if (traj) bp_cn_wave_kernel<DC, true><<<gc, block, 0, st>>>(p);
     else bp_cn_wave_kernel<DC, false><<<gc, block, 0, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
     if (traj) bp_vn_wave_kernel<DV, true><<<gv, block, 0, st>>>(p);

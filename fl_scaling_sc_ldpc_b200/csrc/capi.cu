@@ -153,6 +153,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.thr = c.take<u64>(G);
     q.known = c.take<int32_t>(d->L);
     if (flags & SCLDPC_F_STREAM) q.x = c.take<u128>(G * n * ch);      // stream mode owns its decision plane
+    q.cn_dis = c.take<u128>(G * nk * ch);                             // sized for the largest possible ignored head
     if (p) *p = q;
     return c.off;
 }
@@ -378,6 +379,16 @@ static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool 
     return 0;
 }
 
+// CNs [0, n) are "unscanned" in the next scldpc_bp_full calls of this thread (simulate_sc_ldpc with is_bounded = False:
+// slots below ignored_head_schedule*cns_per_pos are never scanned, PD.py:604-605,656); 0 switches it off.
+static thread_local int g_unscanned_cns = 0;
+extern "C" int scldpc_bp_set_unscanned_head(int n_cns)
+{
+    if (n_cns < 0) return fail(SCLDPC_EINVAL, "n_cns must be >= 0");
+    g_unscanned_cns = n_cns;
+    return 0;
+}
+
 extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
                               const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                               int *iters_launched_host, void *stream)
@@ -398,7 +409,10 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     p.win_edges = 2ll * p.E;
     int launched = 0;
     // wave tracking (bp_wave_kernels.cu) unless disabled or the chain is longer than its shared-memory bitmaps
-    const bool wave = d->L + d->dv - 1 <= 1024 && !env_int("SCLDPC_NO_WAVE", 0, 0, 1);
+    const bool wave = d->L + d->dv - 1 <= 1024 && (!env_int("SCLDPC_NO_WAVE", 0, 0, 1) || g_unscanned_cns > 0);
+    p.cn_dis_lim = g_unscanned_cns;
+    if (g_unscanned_cns > 0 && (!wave || traj || g_unscanned_cns > p.nk))
+        return fail(SCLDPC_EINVAL, "unscanned head: not available with trajectories or for this chain length");
     p.cn_pos_lim = term ? d->L + d->dv - 1 : d->L;
     if (wave) bp_launch_wave_init(p, st);
     if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, wave, st, &launched))) return rc;

@@ -141,6 +141,8 @@ struct BpParams {
     int cn_pos_lim;           // CN positions that are ever swept (L+dv-1 terminated, L truncated)
     long long *swept;         // [G][2] CN / VN positions swept, summed over iterations (instrumentation)
     const u64 *lane_mask;     // [G][W] finalisation kernels only look at these lanes (NULL: all lanes)
+    u128 *cn_dis;             // [G][cn_dis_lim][chunks] CNs below cn_dis_lim that started with exactly one erased neighbour
+    int cn_dis_lim;           //   never resolve it (simulate_sc_ldpc with an ignored head, PD.py:604-605,656); 0 = off
     // frame streams (lane recycling): a finished frame frees its bit lane for the next channel realisation
     u64 *arm_mask;            // [G][W] lanes that take a new frame in the next VN sweep
     u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested

@@ -15,7 +15,7 @@ probability, "fuckup" = frame error.  M is the number of VNs per position.
 Differences, all additive: randomness comes from counter-based Philox streams (``set_seed``) instead of NumPy's /
 ``random``'s global state, so a run does not depend on how frames are batched or split over GPUs; keyword-only
 arguments (``seed``, ``frames_per_graph``, ``first_frame``) were added.  The protograph ensemble (``is_protograph``)
-and the unbounded variant (``is_bounded=False``) are not implemented yet and raise.
+is not implemented yet and raises.
 """
 from __future__ import annotations
 
@@ -203,13 +203,10 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
     flooding BP; that is what runs on the GPU.  Frames are decoded in batches and then accounted in frame order, so
     the ``max_fuckups`` early stop (PD.py:698) cuts at the same frame as a sequential run would."""
     _check_ensemble(is_protograph)
-    if not is_bounded:
-        raise NotImplementedError("is_bounded=False (ignored head, PD.py:604-605) is not implemented yet")
-    if is_tail_biting and is_terminated:
-        pass  # the reference accepts the combination; the tail-biting graph simply has no CN positions beyond L
     seed = _state["seed"] if seed is None else seed
     is_soft = isinstance(doping_points, dict)
-    ignored_head = 0
+    ignored_head = 0 if is_bounded else 20                      # PD.py:604-606
+    ignored_head_schedule = 0 if is_bounded else 10
     ignored_tail = 0 if is_terminated else 20
     L = L + ignored_head + ignored_tail
     cns_per_pos = int(l / r * M)
@@ -246,8 +243,14 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
             fb = engine.FrameBatch(ens, G, fpg, nw)
             fb.generate_graphs(seed, first_graph_id=gid0, tail_biting=bool(is_tail_biting))
             fb.generate_erasures(e, seed + 1, first_graph_id=gid0, doping_points=doping_points)
-        # non-terminated: the decoder never uses CNs >= total_size (truncated BP, BP_TRAJ.c:944-948 semantics)
-        res = engine.decode_bp_full(fb, engine.UNLIMITED, is_term=bool(is_terminated) and not is_tail_biting)
+        # non-terminated: the decoder never uses CNs >= total_size (truncated BP, BP_TRAJ.c:944-948 semantics).
+        # unbounded: slots below ignored_head_schedule*cns_per_pos are never scanned (PD.py:656), they only decode
+        # when a removal leaves them with one user -- scldpc_bp_set_unscanned_head
+        _lib.check(_lib.lib().scldpc_bp_set_unscanned_head(ignored_head_schedule * cns_per_pos))
+        try:
+            res = engine.decode_bp_full(fb, engine.UNLIMITED, is_term=bool(is_terminated) and not is_tail_biting)
+        finally:
+            _lib.lib().scldpc_bp_set_unscanned_head(0)
         words = res.erased_words                                         # [G][n][W] on the device
         transmissions = None
         for g in range(G):

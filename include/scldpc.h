@@ -118,6 +118,12 @@ int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, 
                    const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                    int *iters_launched_host, void *stream);
 
+/* simulate_sc_ldpc with is_bounded = False (PD.py:604-605,656): slots below ignored_head_schedule*cns_per_pos are never
+ * scanned, they only decode when a removal leaves them with one user.  In BP terms a CN below n_cns that starts with
+ * exactly one erased neighbour keeps sending erasures.  Applies to the following scldpc_bp_full calls of the calling
+ * thread; n_cns = 0 switches it off. */
+int scldpc_bp_set_unscanned_head(int n_cns);
+
 /* Frame streams (lane recycling).  Each graph of the batch decodes frames 0 .. frames_per_graph-1 of its channel
  * stream (the same realisations scldpc_channel_generate produces for those frame ids) with unlimited-iteration full
  * BP; d->n_frames lanes per graph are used, and a lane whose frame has stopped is harvested and re-armed with the next

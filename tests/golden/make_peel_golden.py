@@ -60,17 +60,19 @@ def main():
         arrays[name + "_r1"] = r1.astype(np.int32)
         arrays[name + "_plrs"] = plrs
     # ---- error rates ----
-    cases = [("s0", 0.47, 4, 8, 12, 40, True), ("s1", 0.45, 4, 8, 10, 32, False), ("s2", 0.50, 4, 8, 8, 24, True)]
-    for name, e, l, r, L, M, term in cases:
-        Leff = L + (0 if term else 20)
+    cases = [("s0", 0.47, 4, 8, 12, 40, True, True), ("s1", 0.45, 4, 8, 10, 32, False, True), ("s2", 0.50, 4, 8, 8, 24, True, True),
+             ("u0", 0.42, 4, 8, 10, 32, True, False), ("u1", 0.37, 4, 8, 6, 24, False, False),
+             ("u2", 0.44, 4, 8, 8, 40, True, False)]                                            # u*: is_bounded = False
+    for name, e, l, r, L, M, term, bounded in cases:
+        Leff = L + (0 if term else 20) + (0 if bounded else 20)
         frames = []
         for f in range(12):
             tr = ref_code(pd, l, r, Leff, M, rng)
             er = rng.random(Leff * M) <= e
             frames.append((tr, er))
         with redirect_stdout(io.StringIO()):
-            out = pr.ref_simulate_sc_ldpc(e, l, r, L, M, term, True, frames)
-        arrays[name + "_params"] = np.array([e, l, r, L, M, int(term)], np.float64)
+            out = pr.ref_simulate_sc_ldpc(e, l, r, L, M, term, bounded, frames)
+        arrays[name + "_params"] = np.array([e, l, r, L, M, int(term), int(bounded)], np.float64)
         arrays[name + "_tr"] = np.array([f[0] for f in frames], np.int32)
         arrays[name + "_er"] = np.packbits(np.array([f[1] for f in frames], np.uint8), axis=1)
         arrays[name + "_out"] = np.array([out[i] for i in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12)], np.float64)

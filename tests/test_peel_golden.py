@@ -13,7 +13,7 @@ PEEL_SEED = 777
 
 
 def _params(name):
-    e, l, r, L, M, term = Z[name + "_params"]
+    e, l, r, L, M, term = Z[name + "_params"][:6]
     return float(e), int(l), int(r), int(L), int(M), bool(term)
 
 
@@ -35,28 +35,30 @@ def test_oracle_peel_trajectory_matches_reference(name):
         assert abs((er.sum() - rec) / total_generated - Z[name + "_plrs"][f]) < 1e-15
 
 
-@pytest.mark.parametrize("name", ["s0", "s1", "s2"])
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "u0", "u1", "u2"])
 def test_error_rate_bookkeeping_matches_reference(name):
     """product bookkeeping (counted_positions / account_lost / extract_stopping_sets) fed by the oracle's fixed point"""
     e, l, r, L, M, term = _params(name)
+    bounded = bool(Z[name + "_params"][6])
     tail = 0 if term else 20
-    Leff = L + tail
+    head, head_sched = (0, 0) if bounded else (20, 10)
+    Leff = L + tail + head
     cns = int(l / r * M)
     num_positions = Leff + l - 1 if term else Leff
     total_size = cns * num_positions
-    counted = np.repeat(pdx.counted_positions(l, Leff, num_positions, 0, tail), M)
+    counted = np.repeat(pdx.counted_positions(l, Leff, num_positions, head, tail), M)
     nf = nft = fail = fail_e = blocks_e = 0
     F = Z[name + "_tr"].shape[0]
     for f in range(F):
         tr = Z[name + "_tr"][f]
         er = np.unpackbits(Z[name + "_er"][f])[: Leff * M]
-        lost_mask = oracle.peel_fixed_point(tr, er, cns * (Leff + l - 1), 0, total_size).astype(bool) & counted
+        lost_mask = oracle.peel_fixed_point(tr, er, cns * (Leff + l - 1), head_sched * cns, total_size).astype(bool) & counted
         lost = np.flatnonzero(lost_mask)
         if len(lost):
             n, big, le, be = pdx.account_lost(lost, tr.astype(np.int64), M)
             nf += 1; nft += int(big); fail += n; fail_e += le; blocks_e += be
-    gen = (Leff - tail) * M * F
-    blocks = (Leff - tail) * F
+    gen = (Leff - tail - head) * M * F
+    blocks = (Leff - tail - head) * F
     exp = Z[name + "_out"]   # FER, FER_exp, PLR, PLR_exp, n_failed_exp, n_frames, n_vn_failed_exp, n_vn_gen, blocks_failed_exp, blocks_gen, BLER_exp
     got = [nf / F, nft / F, fail / gen, fail_e / gen, nft, F, fail_e, gen, blocks_e, blocks, blocks_e / blocks]
     assert np.allclose(got, exp, rtol=0, atol=1e-15), (got, list(exp))

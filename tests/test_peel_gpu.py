@@ -16,7 +16,7 @@ PEEL_SEED = 777
 
 
 def _params(name):
-    e, l, r, L, M, term = Z[name + "_params"]
+    e, l, r, L, M, term = Z[name + "_params"][:6]
     return float(e), int(l), int(r), int(L), int(M), bool(term)
 
 
@@ -106,12 +106,13 @@ def test_simulate_peeling_decoder_ldpc_signature_and_shapes():
         pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, True, 2)
 
 
-@pytest.mark.parametrize("name", ["s0", "s1", "s2"])
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "u0", "u1", "u2"])
 def test_simulate_sc_ldpc_matches_reference(name):
-    """the 13-tuple of the reference's simulate_sc_ldpc on the same injected codes and erasure masks"""
+    """the 13-tuple of the reference's simulate_sc_ldpc on the same injected codes and erasure masks (u*: unbounded)"""
     e, l, r, L, M, term = _params(name)
+    bounded = bool(Z[name + "_params"][6])
     tail = 0 if term else 20
-    Leff = L + tail
+    Leff = L + tail + (0 if bounded else 20)
     tr_all = Z[name + "_tr"]
     er_all = np.unpackbits(Z[name + "_er"], axis=1)[:, : Leff * M]
     F = tr_all.shape[0]
@@ -121,7 +122,7 @@ def test_simulate_sc_ldpc_matches_reference(name):
         fb = eng.FrameBatch(ens, G, 1, 2).set_graphs(tr_all[gid0:gid0 + G])
         return fb.set_erasures(er_all[gid0:gid0 + G, None, :])
 
-    out = pdx.simulate_sc_ldpc(e, l, r, L, M, term, False, True, False, F, 10 ** 9, [], frames_per_graph=1, graphs_per_batch=5,
+    out = pdx.simulate_sc_ldpc(e, l, r, L, M, term, False, bounded, False, F, 10 ** 9, [], frames_per_graph=1, graphs_per_batch=5,
                                progress=False, _batch_factory=factory)
     got = [out[i] for i in (0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12)]
     assert np.allclose(got, Z[name + "_out"], rtol=0, atol=1e-15), (got, list(Z[name + "_out"]))
