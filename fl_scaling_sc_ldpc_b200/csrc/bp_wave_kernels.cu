@@ -330,8 +330,9 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
 //   harvest : every few iterations the finalisation kernels run on done_mask only, results are stored under the
 //             frame id, and the freed lanes get the next frame ids in ascending lane order (deterministic).
 // Only unlimited-iteration decoding streams (a capped frame would keep changing while it waits for the harvest).
-template <int DV>
-__global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
+// ARM = false is the lean variant for iterations in which no lane takes a new frame (15 of 16).
+template <int DV, bool ARM>
+__global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    const u128 arm = reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k];
+    const u128 arm = ARM ? reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k] : zero128();
     const bool lane_work = nz(act | arm);
     u128 acc_new = zero128(), acc_er = zero128();   // every position is swept, so "an erased VN is left" is a plain OR
     const u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * p.dc * ch;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
     const int32_t *__restrict__ vn_slot = p.vn_slot + (size_t)g * p.n * DV;
     const int items = p.n << p.chunk_shift;
     const int stride = gridDim.x * blockDim.x;
-    const u64 thr = nz(arm) ? p.thr[g] : 0ull;
+    const u64 thr = (ARM && nz(arm)) ? p.thr[g] : 0ull;
     const uint64_t gid = p.first_graph + (uint64_t)g;
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
         const int idx = base + (threadIdx.x & 31);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
             for (int i = DV - 1; i >= 0; i--) { out[i] &= acc; acc &= in[i]; }
 #pragma unroll
             for (int i = 0; i < DV; i++) yn |= out[i];
-            if (nz(arm)) {
+            if (ARM && nz(arm)) {
                 // new frames: Lji = channel value on every edge (BP_FULL.c:913-917), previous decision "all erased"
                 const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
                 u128 cw = zero128();
@@ -404,7 +405,8 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
                 xn = xn | arm;
                 yn = sel(arm, cw, yn);
             }
-            changed = make_u128((((xn.x ^ xo.x) | (yn.x ^ yo.x)) & act.x) | arm.x, (((xn.y ^ xo.y) | (yn.y ^ yo.y)) & act.y) | arm.y);
+            changed = make_u128(((xn.x ^ xo.x) | (yn.x ^ yo.x)) & act.x, ((xn.y ^ xo.y) | (yn.y ^ yo.y)) & act.y);
+            if (ARM) changed |= arm;
         }
         unsigned flag = nz(changed) ? 1u : 0u;
         for (int o = 1; o < ch; o <<= 1) flag |= __shfl_xor_sync(0xffffffffu, flag, o);
@@ -451,8 +453,9 @@ __global__ void __launch_bounds__(256, 3) bp_vn_stream_kernel(BpParams p)
         const u64 stop = a & (~er | ~nw);                      // NumErasures == 0  ||  == NumErasuresPrec
         s_stop[w] = stop;
         s_act[w] = a;
-        p.active[g * W + w] = (a & ~stop) | p.arm_mask[g * W + w];   // armed lanes start iterating with the next sweep
-        p.arm_mask[g * W + w] = 0;
+        u64 left = a & ~stop;
+        if (ARM) { left |= p.arm_mask[g * W + w]; p.arm_mask[g * W + w] = 0; }   // armed lanes start iterating with the next sweep
+        p.active[g * W + w] = left;
         p.done_mask[g * W + w] |= stop;
         p.any_new[g * W + w] = 0;
     }
@@ -592,14 +595,16 @@ int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaS
 }
 
 template <int DV, int DC>
-static void launch_stream_iteration(const BpParams &p, cudaStream_t st)
+static void launch_stream_iteration(const BpParams &p, bool arm, cudaStream_t st)
 {
     const int block = 256;
-    static int res_cn = 0, res_vn = 0;
+    static int res_cn = 0, res_vn_arm = 0, res_vn_lean = 0;
     if (!res_cn) {
         res_cn = resident_blocks(bp_cn_wave_kernel<DC, false>, block);
-        res_vn = resident_blocks(bp_vn_stream_kernel<DV>, block);
+        res_vn_arm = resident_blocks(bp_vn_stream_kernel<DV, true>, block);
+        res_vn_lean = resident_blocks(bp_vn_stream_kernel<DV, false>, block);
     }
+    const int res_vn = arm ? res_vn_arm : res_vn_lean;
     auto grid = [&](int resident, long long items_per_graph) {
         long long need = (items_per_graph + block - 1) / block;
         long long gx = need < resident ? need : resident;
@@ -613,20 +618,22 @@ static void launch_stream_iteration(const BpParams &p, cudaStream_t st)
     g_prof.launches += 2;
     bp_cn_wave_kernel<DC, false><<<gc, block, 0, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
-    bp_vn_stream_kernel<DV><<<gv, block, 0, st>>>(p);
+    if (arm) bp_vn_stream_kernel<DV, true><<<gv, block, 0, st>>>(p);
+    else bp_vn_stream_kernel<DV, false><<<gv, block, 0, st>>>(p);
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
     }
 }
 
-int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, cudaStream_t st)
+// arm: lanes re-armed by the preceding harvest take their new frames in this iteration's VN sweep
+int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st)
 {
-    if (dv == 4 && dc == 8) launch_stream_iteration<4, 8>(p, st);
-    else if (dv == 3 && dc == 6) launch_stream_iteration<3, 6>(p, st);
-    else if (dv == 5 && dc == 10) launch_stream_iteration<5, 10>(p, st);
-    else if (dv == 3 && dc == 9) launch_stream_iteration<3, 9>(p, st);
-    else if (dv == 4 && dc == 12) launch_stream_iteration<4, 12>(p, st);
+    if (dv == 4 && dc == 8) launch_stream_iteration<4, 8>(p, arm, st);
+    else if (dv == 3 && dc == 6) launch_stream_iteration<3, 6>(p, arm, st);
+    else if (dv == 5 && dc == 10) launch_stream_iteration<5, 10>(p, arm, st);
+    else if (dv == 3 && dc == 9) launch_stream_iteration<3, 9>(p, arm, st);
+    else if (dv == 4 && dc == 12) launch_stream_iteration<4, 12>(p, arm, st);
     else return -1;
     return 0;
 }

@@ -19,7 +19,7 @@ void bp_launch_window_begin(const BpParams &p, int n_frames, cudaStream_t st);
 void bp_launch_init_ctrl_only(const BpParams &p, int n_frames, cudaStream_t st);
 int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
-int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, cudaStream_t st);
+int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
 int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
@@ -511,7 +511,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     for (;;) {
         for (int q = 0; q < H; q++, it++) {
             p.iter = (int)(it & 0x3fffffff);
-            if (bp_launch_stream_iteration(d->dv, d->dc, p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+            if (bp_launch_stream_iteration(d->dv, d->dc, p, q == 0, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
