@@ -62,8 +62,10 @@ __global__ void bp_init_ctrl_kernel(BpParams p, int n_frames)
     for (int i = threadIdx.x; i < p.L * p.W; i += blockDim.x) p.pos_er[(size_t)g * p.L * p.W + i] = 0;
     for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
         p.iters[g * p.lanes + l] = 0;
-        p.cnt_dvn[g * p.lanes + l] = 0;
-        p.cnt_deg1[g * p.lanes + l] = 0;
+        for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
+            p.cnt_dvn[((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l] = 0;
+            p.cnt_deg1[((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l] = 0;
+        }
         p.work[g * p.lanes + l] = 0;
     }
     for (int i = threadIdx.x; i < p.L * p.lanes; i += blockDim.x) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256) bp_cn_sweep_kernel(BpParams p)
     if (TRAJ) {
         __syncthreads();
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
-            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + g * p.lanes + i, s_cnt[i]);
+            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + ((size_t)g * SCLDPC_CNT_SLOTS + (blockIdx.x % SCLDPC_CNT_SLOTS)) * p.lanes + i, s_cnt[i]);
     }
 }
 
@@ -196,10 +198,14 @@ __device__ void bp_retire_lanes(const BpParams &p, int g)
             p.work[g * p.lanes + l] += (long long)(p.iter + 1) * p.win_edges;
         }
         if (TRAJ) {
-            const int dvn = ld_cg(p.cnt_dvn + g * p.lanes + l);
-            const int d1 = ld_cg(p.cnt_deg1 + g * p.lanes + l);
-            p.cnt_dvn[g * p.lanes + l] = 0;
-            p.cnt_deg1[g * p.lanes + l] = 0;
+            int dvn = 0, d1 = 0;
+            for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
+                const size_t o = ((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l;
+                dvn += ld_cg(p.cnt_dvn + o);
+                d1 += ld_cg(p.cnt_deg1 + o);
+                p.cnt_dvn[o] = 0;
+                p.cnt_deg1[o] = 0;
+            }
             if (((s_act[w] >> b) & 1ull) && p.row >= 0 && p.row < p.max_rows) {
                 int first = p.L;                                        // first_erased = n => prints L (BP_TRAJ.c:1017,1051)
                 for (int q = 0; q < p.L; q++)
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(256) bp_vn_sweep_kernel(BpParams p)
     }
     if (TRAJ)
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
-            if (s_cnt[i]) atomicAdd(p.cnt_dvn + g * p.lanes + i, s_cnt[i]);
+            if (s_cnt[i]) atomicAdd(p.cnt_dvn + ((size_t)g * SCLDPC_CNT_SLOTS + (blockIdx.x % SCLDPC_CNT_SLOTS)) * p.lanes + i, s_cnt[i]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);

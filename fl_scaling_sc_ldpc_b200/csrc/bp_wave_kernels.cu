@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
+    __shared__ u128 s_planes[TRAJ ? LC_PLANES * 256 : 1];
     if (TRAJ) {
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
         __syncthreads();
@@ -60,12 +61,18 @@ __global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel
     u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * DC * ch;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
     const int *__restrict__ list = p.cn_list + g * (p.L + p.dv - 1);
+    LaneCounter lc;
+    if (TRAJ) lc.clear();
 
-    if (nz(act)) {
-        const int ipp = p.cns_pos << p.chunk_shift;                 // work items per position
-        const int items = ld_cg(p.n_list + 2 * g) * ipp;
-        const int stride = gridDim.x * blockDim.x;
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+    const bool lane_work = nz(act);
+    const int ipp = p.cns_pos << p.chunk_shift;                 // work items per position
+    const int items = ld_cg(p.n_list + 2 * g) * ipp;
+    const int stride = gridDim.x * blockDim.x;
+    // In trajectory mode the trip count is block-uniform (the counter flush below is a block-wide step).
+    int trip = 0;
+    for (int base = blockIdx.x * blockDim.x; base < items; base += stride, trip++) {
+        const int idx = base + threadIdx.x;
+        if (lane_work && idx < items) {
             const int ent = idx / ipp, off = idx - ent * ipp;
             const int c = __ldg(list + ent) * p.cns_pos + (off >> p.chunk_shift);
             int e[DC];
@@ -100,6 +107,7 @@ __global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel
 #pragma unroll
             for (int j = 0; j < DC; j++) dst[(size_t)j * ch] = out[j];
             if (TRAJ) {
+                // degree-one counter with latch (BP_FULL.c:935-979): num_out_resolved = #j with out[j] == 0
                 u128 one = zero128(), two = zero128();
 #pragma unroll
                 for (int j = 0; j < DC; j++) {
@@ -107,17 +115,17 @@ __global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel
                 }
                 u128 *lp = p.latch + ((size_t)g * p.nk + c) * ch + k;
                 const u128 lat = *lp;
-                const u128 cnt = one & ~two & ~lat & act;
                 const u128 nl = lat | (one & act);
                 if (neq(nl, lat)) *lp = nl;
-                if (nz(cnt)) sparse_count(s_cnt, k * 128, cnt);
+                lc.add(one & ~two & ~lat & act);
             }
         }
+        if (TRAJ && (trip % 31) == 30) lane_counter_flush(lc, s_planes, s_cnt, ch);
     }
     if (TRAJ) {
-        __syncthreads();
+        lane_counter_flush(lc, s_planes, s_cnt, ch);
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
-            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + g * p.lanes + i, s_cnt[i]);
+            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + ((size_t)g * SCLDPC_CNT_SLOTS + (blockIdx.x % SCLDPC_CNT_SLOTS)) * p.lanes + i, s_cnt[i]);
     }
 }
 
@@ -161,10 +169,14 @@ __device__ void bp_wave_retire(const BpParams &p, int g)
         const int w = l >> 6, b = l & 63;
         if ((s_stop[w] >> b) & 1ull) p.iters[g * p.lanes + l] += p.iter + 1;
         if (TRAJ) {
-            const int dvn = ld_cg(p.cnt_dvn + g * p.lanes + l);
-            const int d1 = ld_cg(p.cnt_deg1 + g * p.lanes + l);
-            p.cnt_dvn[g * p.lanes + l] = 0;
-            p.cnt_deg1[g * p.lanes + l] = 0;
+            int dvn = 0, d1 = 0;
+            for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
+                const size_t o = ((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l;
+                dvn += ld_cg(p.cnt_dvn + o);
+                d1 += ld_cg(p.cnt_deg1 + o);
+                p.cnt_dvn[o] = 0;
+                p.cnt_deg1[o] = 0;
+            }
             if (((s_act[w] >> b) & 1ull) && p.row >= 0 && p.row < p.max_rows) {
                 int first = L;
                 for (int q = 0; q < L; q++)
@@ -212,12 +224,15 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
+    __shared__ u128 s_planes[TRAJ ? LC_PLANES * 256 : 1];
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
     if (TRAJ)
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
     __syncthreads();
+    LaneCounter lc;
+    if (TRAJ) lc.clear();
 
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
@@ -235,10 +250,11 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
     const int ipp = p.vns_pos << p.chunk_shift;
     const int items = ld_cg(p.n_list + 2 * g + 1) * ipp;
     const int stride = gridDim.x * blockDim.x;
-    // The trip count is warp-uniform because the row-write decision below is a shuffle over the ch adjacent threads
-    // that hold one VN.
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
-        const int idx = base + (threadIdx.x & 31);
+    // The trip count is block-uniform: the row-write decision below is a shuffle over the ch adjacent threads that hold
+    // one VN, and in trajectory mode the counter flush is a block-wide step.
+    int trip = 0;
+    for (int base = blockIdx.x * blockDim.x; base < items; base += stride, trip++) {
+        const int idx = base + threadIdx.x;
         const bool work = lane_work && idx < items;
         u128 changed = zero128(), xn = zero128(), yn = zero128(), xo = zero128(), yo = zero128();
         u128 out[DV];
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
             }
             const u128 newly = xo & ~xn & act;
             acc_new |= newly;
-            if (TRAJ && nz(newly)) sparse_count(s_cnt, k * 128, newly);
+            if (TRAJ) lc.add(newly);
             const u128 er = xn & act;
             if (nz(er)) {
                 u64 *pe = p.pos_er_new + ((size_t)g * p.L + pos) * p.W + 2 * k;
@@ -293,7 +309,9 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
                 if (er.y & ~ld_cg(pe + 1)) atomicOr(pe + 1, er.y);
             }
         }
+        if (TRAJ && (trip % 31) == 30) lane_counter_flush(lc, s_planes, s_cnt, ch);
     }
+    if (TRAJ) lane_counter_flush(lc, s_planes, s_cnt, ch);
     acc_new = warp_or_same_chunk(acc_new, ch);
     if ((threadIdx.x & 31) < ch) {
         if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
@@ -306,7 +324,7 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
     }
     if (TRAJ)
         for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
-            if (s_cnt[i]) atomicAdd(p.cnt_dvn + g * p.lanes + i, s_cnt[i]);
+            if (s_cnt[i]) atomicAdd(p.cnt_dvn + ((size_t)g * SCLDPC_CNT_SLOTS + (blockIdx.x % SCLDPC_CNT_SLOTS)) * p.lanes + i, s_cnt[i]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);

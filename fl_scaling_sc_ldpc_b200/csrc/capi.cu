@@ -133,8 +133,8 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.ticket = c.take<unsigned>(G);
     q.alive = c.take<int>(G);
     q.alive_total = c.take<int>(1);
-    q.cnt_dvn = c.take<int>(G * lanes);
-    q.cnt_deg1 = c.take<int>(G * lanes);
+    q.cnt_dvn = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
+    q.cnt_deg1 = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
     q.pos_cnt = c.take<int>(G * d->L * lanes);
     q.pos_pairs = c.take<int>(G * d->L * lanes);
     q.work = c.take<long long>(G * lanes);
