@@ -26,8 +26,8 @@ int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
 int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge, int32_t *scratch, int *err_dev, int G,
                        int n, int nk, int dv, int dc, cudaStream_t st);
 int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
-                   uint64_t first_graph, int tail_biting, cudaStream_t st);
-size_t graph_generate_scratch_words(int G, int L, int cns_pos, int dv, int dc, int tail_biting);
+                   uint64_t first_graph, int ensemble, cudaStream_t st);
+size_t graph_generate_scratch_words(int G, int L, int vns_pos, int cns_pos, int dv, int dc, int ensemble);
 void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
                       uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st);
 void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
@@ -251,7 +251,7 @@ extern "C" int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev,
     if ((rc = have_device())) return rc;
     if (graph_generate(vn_cn_dev, reinterpret_cast<u64 *>(scratch_dev), d->n_graphs, d->L, d->vns_pos, d->cns_pos, d->dv,
                        d->dc, seed, first_graph_id, tail_biting, static_cast<cudaStream_t>(stream)))
-        return fail(SCLDPC_EINVAL, "cns_pos*dc too large for the key layout");
+        return fail(SCLDPC_EINVAL, "cns_pos*dc too large for the key layout, or M not a multiple of cns_pos (protograph)");
     CU(cudaGetLastError());
     return 0;
 }
@@ -259,7 +259,7 @@ extern "C" int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev,
 extern "C" size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting)
 {
     if (check_dims(d)) return 0;
-    return sizeof(u64) * graph_generate_scratch_words(d->n_graphs, d->L, d->cns_pos, d->dv, d->dc, tail_biting);
+    return sizeof(u64) * graph_generate_scratch_words(d->n_graphs, d->L, d->vns_pos, d->cns_pos, d->dv, d->dc, tail_biting);
 }
 
 // doping description -> per-position count of leading VNs that are known (hard: all of them; soft: int(alpha*M))

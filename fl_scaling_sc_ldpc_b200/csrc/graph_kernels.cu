@@ -148,15 +148,38 @@ __global__ void graph_from_keys_kernel(const u64 *keys, int32_t *vn_cn, int Spad
     }
 }
 
-int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
-                   uint64_t first_graph, int tail_biting, cudaStream_t st)
+// Protograph-based ensemble (sc_ldpc_protograph.py:6-20, used at PD.py:198-239): the M VNs of a position form M/cns_pos
+// portions of cns_pos VNs; edge i of VN t of a portion goes to CN perm[t] of position p+i, with an independent uniform
+// permutation of the cns_pos CNs per (position, portion, edge type).  keys holds one sorted segment per permutation.
+__global__ void graph_from_keys_proto_kernel(const u64 *keys, int32_t *vn_cn, int Spad, int L, int vns_pos, int cns_pos, int dv)
 {
-    const int S = cns_pos * dc;
+    const int g = blockIdx.y;
+    const int portions = vns_pos / cns_pos;
+    const long long E = (long long)L * vns_pos * dv;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % dv);
+        const long long v = e / dv;
+        const int pos = (int)(v / vns_pos), tt = (int)(v % vns_pos);
+        const int portion = tt / cns_pos, t = tt % cns_pos;
+        const size_t seg = (((size_t)g * L + pos) * portions + portion) * dv + i;
+        const u64 key = keys[seg * Spad + t];
+        vn_cn[(size_t)g * E + e] = (pos + i) * cns_pos + (int)(key & ((1ull << KEY_IDX_BITS) - 1));
+    }
+}
+
+// ensemble: 0 = semi-structured (generate_code / SC.gen_slots), 1 = its tail-biting variant, 2 = protograph-based
+int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
+                   uint64_t first_graph, int ensemble, cudaStream_t st)
+{
+    const bool proto = ensemble == 2;
+    const int tail_biting = ensemble == 1;
+    if (proto && (vns_pos % cns_pos)) return -1;
+    const int S = proto ? cns_pos : cns_pos * dc;
     if (S > (1 << KEY_IDX_BITS)) return -1;
     int lg = 1;
     while ((1 << lg) < S) lg++;
     const int Spad = 1 << lg;
-    const int npos = tail_biting ? L : L + dv - 1;
+    const int npos = proto ? L * (vns_pos / cns_pos) * dv : (tail_biting ? L : L + dv - 1);   // segments per graph
     const int segs = G * npos;
     unsigned bx = (unsigned)((Spad / 2 + 255) / 256);
     if (bx > 64) bx = 64;
@@ -173,16 +196,19 @@ int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns
     }
     const long long E = (long long)L * vns_pos * dv;
     unsigned be = (unsigned)((E + 255) / 256 < 1184 ? (E + 255) / 256 : 1184);
-    graph_from_keys_kernel<<<dim3(be, G), 256, 0, st>>>(keys, vn_cn, Spad, npos, L, vns_pos, cns_pos, dv, dc, tail_biting);
+    if (proto) graph_from_keys_proto_kernel<<<dim3(be, G), 256, 0, st>>>(keys, vn_cn, Spad, L, vns_pos, cns_pos, dv);
+    else graph_from_keys_kernel<<<dim3(be, G), 256, 0, st>>>(keys, vn_cn, Spad, npos, L, vns_pos, cns_pos, dv, dc, tail_biting);
     return 0;
 }
 
-size_t graph_generate_scratch_words(int G, int L, int cns_pos, int dv, int dc, int tail_biting)
+size_t graph_generate_scratch_words(int G, int L, int vns_pos, int cns_pos, int dv, int dc, int ensemble)
 {
-    const int S = cns_pos * dc;
+    const bool proto = ensemble == 2;
+    const int S = proto ? cns_pos : cns_pos * dc;
     int lg = 1;
     while ((1 << lg) < S) lg++;
-    return (size_t)G * (tail_biting ? L : L + dv - 1) * ((size_t)1 << lg);
+    const size_t segs = proto ? (size_t)L * (vns_pos / (cns_pos > 0 ? cns_pos : 1)) * dv : (size_t)(ensemble == 1 ? L : L + dv - 1);
+    return (size_t)G * segs * ((size_t)1 << lg);
 }
 
 // ------------------------------------------------------------------------------------------------------------

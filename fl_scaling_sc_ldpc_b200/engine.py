@@ -97,9 +97,12 @@ class FrameBatch:
         self._build_tables()
         return self
 
-    def generate_graphs(self, seed: int, first_graph_id: int = 0, tail_biting: bool = False) -> "FrameBatch":
-        """Draw graphs on the device (``generate_code`` BP_FULL.c:1656 / ``SC.gen_slots`` SC.py:53)."""
+    def generate_graphs(self, seed: int, first_graph_id: int = 0, tail_biting: bool = False, protograph: bool = False) -> "FrameBatch":
+        """Draw graphs on the device: the semi-structured ensemble (``generate_code`` BP_FULL.c:1656 / ``SC.gen_slots``
+        SC.py:53), its tail-biting variant, or the protograph-based ensemble (``sc_ldpc_protograph.py``)."""
         L = _lib.lib()
+        ensemble = 2 if protograph else int(bool(tail_biting))
+        tail_biting = ensemble
         nbytes = L.scldpc_graph_generate_scratch_bytes(ctypes.byref(self.dims), int(tail_biting))
         if self._keys is None or self._keys.numel() * 8 < nbytes:
             self._keys = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device)

@@ -14,8 +14,8 @@ probability, "fuckup" = frame error.  M is the number of VNs per position.
 
 Differences, all additive: randomness comes from counter-based Philox streams (``set_seed``) instead of NumPy's /
 ``random``'s global state, so a run does not depend on how frames are batched or split over GPUs; keyword-only
-arguments (``seed``, ``frames_per_graph``, ``first_frame``) were added.  The protograph ensemble (``is_protograph``)
-is not implemented yet and raises.
+arguments (``seed``, ``frames_per_graph``, ``first_frame``) were added.  Both ensembles are available (``is_protograph``);
+the two protograph combinations that are broken upstream (soft doping, tail-biting) raise.
 """
 from __future__ import annotations
 
@@ -56,9 +56,13 @@ class _Progress:
             self.bar.close()
 
 
-def _check_ensemble(is_protograph):
-    if is_protograph:
-        raise NotImplementedError("the protograph ensemble (sc_ldpc_protograph.py) is not implemented yet")
+def _check_ensemble(is_protograph, doping_points=(), is_tail_biting=False):
+    """The reference's protograph path has two upstream defects that are not reproduced: soft doping raises a NameError
+    (PD.py:227, undefined ``position``) and tail-biting takes CN indices modulo L instead of modulo L*cns (PD.py:205)."""
+    if is_protograph and (isinstance(doping_points, dict) and len(doping_points) > 0):
+        raise NotImplementedError("soft doping of the protograph ensemble is broken upstream (PD.py:227)")
+    if is_protograph and is_tail_biting:
+        raise NotImplementedError("tail-biting protograph ensemble is broken upstream (PD.py:205)")
 
 
 def _doping_count(doping_points):
@@ -111,7 +115,7 @@ def simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_proto
     degree-one CNs after every peeling step, ``plrs`` float64 [num_repeats] the fraction of VNs left erased.
 
     The reference draws a new code per frame; ``frames_per_graph`` (default 1) keeps that."""
-    _check_ensemble(is_protograph)
+    _check_ensemble(is_protograph, doping_points)
     if not num_repeats:
         num_repeats = 100
     seed = _state["seed"] if seed is None else seed
@@ -132,7 +136,7 @@ def simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_proto
         G = min(graphs_per_batch, (left + fpg - 1) // fpg)
         gid0 = (first_frame + done) // fpg
         fb = engine.FrameBatch(ens, G, fpg, 2)
-        fb.generate_graphs(seed, first_graph_id=gid0)
+        fb.generate_graphs(seed, first_graph_id=gid0, protograph=bool(is_protograph))
         fb.generate_erasures(e, seed + 1, first_graph_id=gid0, doping_points=doping_points)
         r1_t, rec, ner = peel_batch(ens, fb, total_size, num_pd_steps, seed + 2, first_frame + done)
         k = min(left, G * fpg)
@@ -202,7 +206,7 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
     The in-order ``sic_round`` scan (PD.py:656-657) reaches the peeling fixed point, which is the residual of unlimited
     flooding BP; that is what runs on the GPU.  Frames are decoded in batches and then accounted in frame order, so
     the ``max_fuckups`` early stop (PD.py:698) cuts at the same frame as a sequential run would."""
-    _check_ensemble(is_protograph)
+    _check_ensemble(is_protograph, doping_points, is_tail_biting)
     seed = _state["seed"] if seed is None else seed
     is_soft = isinstance(doping_points, dict)
     ignored_head = 0 if is_bounded else 20                      # PD.py:604-606
@@ -241,7 +245,7 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
             fb = _batch_factory(ens, G, fpg, gid0)
         else:
             fb = engine.FrameBatch(ens, G, fpg, nw)
-            fb.generate_graphs(seed, first_graph_id=gid0, tail_biting=bool(is_tail_biting))
+            fb.generate_graphs(seed, first_graph_id=gid0, tail_biting=bool(is_tail_biting), protograph=bool(is_protograph))
             fb.generate_erasures(e, seed + 1, first_graph_id=gid0, doping_points=doping_points)
         # non-terminated: the decoder never uses CNs >= total_size (truncated BP, BP_TRAJ.c:944-948 semantics).
         # unbounded: slots below ignored_head_schedule*cns_per_pos are never scanned (PD.py:656), they only decode

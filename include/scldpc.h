@@ -91,8 +91,9 @@ int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_batch_t *b, i
 /* On-device ensemble generation: the "Olmos random ensemble" of generate_code (BP_FULL.c:1656-1761) /
  * SC.gen_slots (SC.py:33-56): an independent uniform socket permutation per CN position.  Graph g of the batch
  * is realisation first_graph_id+g of stream `seed` (Philox4x32-10), independent of the batch / GPU layout.
- * tail_biting != 0 gives SC.gen_slots_tail_biting (SC.py:41-45, nk = L*cns_pos).  scratch_dev: uint64
- * [G][L+dv-1][cns_pos*dc] sort keys. */
+ * The last argument selects the ensemble: 0 = semi-structured, 1 = its tail-biting variant SC.gen_slots_tail_biting
+ * (SC.py:41-45, nk = L*cns_pos), 2 = protograph-based (sc_ldpc_protograph.py:6-20: per (position, portion, edge type) a
+ * uniform permutation of the cns_pos CNs).  scratch_dev: sort keys, scldpc_graph_generate_scratch_bytes bytes. */
 int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
                           uint64_t first_graph_id, int tail_biting, void *stream);
 size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting);

@@ -102,8 +102,10 @@ def test_simulate_peeling_decoder_ldpc_signature_and_shapes():
     assert (r1 == r1b).all() and (plrs == plrsb).all()                      # reproducible
     _, r1c, _ = pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, False, 6, [5, 6], seed=1)
     assert r1c.shape == r1.shape
+    _, r1p, plrsp = pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, True, 4, seed=1)       # protograph ensemble
+    assert r1p.shape == (4, r1.shape[1]) and (plrsp >= 0).all()
     with pytest.raises(NotImplementedError):
-        pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, True, 2)
+        pdx.simulate_peeling_decoder_ldpc(0.46, 4, 8, 12, 40, False, True, 2, {3: 0.5})                 # broken upstream
 
 
 @pytest.mark.parametrize("name", ["s0", "s1", "s2", "u0", "u1", "u2"])
@@ -156,6 +158,30 @@ def test_generated_ensemble_is_valid_and_uniformish():
     # different graph ids give different codes; the socket of VN 0 / edge 0 is roughly uniform over the CNs
     firsts = np.array([scx.gen_slots(l, r, L, M)[0, 0] for _ in range(200)])
     assert len(set(firsts.tolist())) > 15 and firsts.max() < cns
+
+
+def test_generated_protograph_ensemble_is_valid():
+    """sc_ldpc_protograph.gen_slots_from_position: per (position, portion, edge type) a permutation of the position's CNs"""
+    l, r, L, M = 4, 8, 7, 48
+    cns = M * l // r
+    ens = eng.Ensemble(l, r, L, M)
+    fb = eng.FrameBatch(ens, 3, 2).generate_graphs(17, protograph=True)
+    tr = fb.vn_cn.cpu().numpy()
+    assert len({tr[g].tobytes() for g in range(3)}) == 3
+    for g in range(3):
+        t = tr[g].reshape(L, M // cns, cns, l)                              # [position][portion][vn][edge]
+        for p in range(L):
+            for q in range(M // cns):
+                for i in range(l):
+                    col = t[p, q, :, i]
+                    assert (col // cns == p + i).all() and sorted((col % cns).tolist()) == list(range(cns))
+        deg = np.bincount(tr[g].reshape(-1), minlength=(L + l - 1) * cns)
+        assert (deg[(l - 1) * cns: L * cns] == r).all()
+    # the decoders run on it unchanged
+    fb.generate_erasures(0.40, 18)
+    assert eng.decode_bp_full(fb, 0, True).residual.shape == (3, 2)
+    out = pdx.simulate_sc_ldpc(0.40, 4, 8, 12, 64, True, True, True, False, 256, 10 ** 9, [], seed=5, progress=False)
+    assert out[5] == 256 and 0.0 <= out[0] <= 1.0
 
 
 def test_generated_channel_statistics_and_doping():
