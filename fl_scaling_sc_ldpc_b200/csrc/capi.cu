@@ -641,6 +641,25 @@ extern "C" int scldpc_peel_variance_accumulate(const int32_t *r1_dev, int n_fram
     return 0;
 }
 
+// Per-position results of the last scldpc_bp_full / scldpc_bp_window call on this workspace (device to device):
+// pos_cnt[g][p][lane] = erased VNs of position p, pos_pairs[g][p][lane] = accepted size-two stopping sets of position p
+// (get_deg_two_ss, BP_FULL.c:1227: the expurgated count of a position is pos_cnt - 2*pos_pairs).
+extern "C" int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, int32_t *pos_cnt_dev,
+                                         int32_t *pos_pairs_dev, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!workspace_dev || !pos_cnt_dev || !pos_pairs_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    BpParams p;
+    carve(d, flags, workspace_dev, &p);
+    const size_t bytes = sizeof(int32_t) * (size_t)d->n_graphs * d->L * 64 * d->n_words;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemcpyAsync(pos_cnt_dev, p.pos_cnt, bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(pos_pairs_dev, p.pos_pairs, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 // ---- instrumentation --------------------------------------------------------------------------------------------
 // Positions swept by the last scldpc_bp_full call on this workspace, summed over graphs and iterations:
 // out[0] = CN positions, out[1] = VN positions (a sweep of everything would be iterations*(L+dv-1) and iterations*L).

@@ -239,6 +239,17 @@ def decode_bp_full(fb: FrameBatch, max_it: int = UNLIMITED, is_term: bool = True
     return r
 
 
+def position_counts(fb: FrameBatch, flags: int):
+    """Per-position erased-VN counts and accepted size-two stopping sets of the last decode on ``fb``:
+    two int32 arrays [n_graphs][L][n_frames]."""
+    G, Lp, lanes = fb.n_graphs, fb.ens.L, 64 * fb.n_words
+    cnt = torch.empty((G, Lp, lanes), dtype=torch.int32, device=fb.device)
+    pairs = torch.empty((G, Lp, lanes), dtype=torch.int32, device=fb.device)
+    _lib.check(_lib.lib().scldpc_bp_position_counts(ctypes.byref(fb.dims), flags, ctypes.c_void_p(fb.workspace(flags).data_ptr()),
+                                                    ctypes.c_void_p(cnt.data_ptr()), ctypes.c_void_p(pairs.data_ptr()), _stream()))
+    return cnt[:, :, :fb.n_frames].cpu().numpy(), pairs[:, :, :fb.n_frames].cpu().numpy()
+
+
 def decode_bp_window(fb: FrameBatch, W: int, max_it: int, init_it: int = 0, square: bool = True, is_term: bool = True,
                      collect: bool = True):
     """Sliding-window BP -- ``decodeBP_SW`` (square window BP_SW.c:628, classical window BP_FULL.c:627)."""

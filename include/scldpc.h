@@ -119,6 +119,13 @@ int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, 
                    const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                    int *iters_launched_host, void *stream);
 
+/* Per-position results of the last scldpc_bp_full / scldpc_bp_window call on this workspace, int32 [G][L][64*W] each:
+ * erased VNs per position and accepted size-two stopping sets per position (get_deg_two_ss, BP_FULL.c:1227-1283: the
+ * expurgated count of a position is pos_cnt - 2*pos_pairs).  These are what main_streaming / decodeBP_SW_circular
+ * accumulate position by position (BP_FULL.c:1483-1497, :2015-2031). */
+int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, int32_t *pos_cnt_dev,
+                              int32_t *pos_pairs_dev, void *stream);
+
 /* simulate_sc_ldpc with is_bounded = False (PD.py:604-605,656): slots below ignored_head_schedule*cns_per_pos are never
  * scanned, they only decode when a removal leaves them with one user.  In BP terms a CN below n_cns that starts with
  * exactly one erased neighbour keeps sending erasures.  Applies to the following scldpc_bp_full calls of the calling

@@ -140,6 +140,33 @@ def decode_bp_sw(g: Graph, chan: np.ndarray, W: int, max_it: int, init_it: int =
                 blocks_err_exp=nbe.value, erased=erased, win_iters=win_iters, v2c=lji, c2v=lij)
 
 
+def position_counts(g: Graph, erased: np.ndarray):
+    """``orc_position_counts``: per position (erased VNs, expurgated erased VNs as in ``get_deg_two_ss``)."""
+    erased = np.ascontiguousarray(erased, np.uint8)
+    plain = np.zeros(g.L, np.int32)
+    ex = np.zeros(g.L, np.int32)
+    lib().orc_position_counts(g.n, g.nk, g.L, g.vns_pos, g.dv, g.dc, _ptr(g.vn_cn), _ptr(g.cn_deg), _ptr(g.cn_vn), _ptr(erased),
+                              _ptr(plain), _ptr(ex))
+    return plain, ex
+
+
+def stream_counters(plain: np.ndarray, ex: np.ndarray, n_steps: int, dv: int):
+    """main_streaming's running counters (BP_FULL.c:2015-2031, decodeBP_SW_circular :1483-1497) after each of n_steps
+    decode steps, from per-position counts: step `pos` decides absolute position pos-dv+1 and expurgates pos-2*dv+1.
+    Returns int64 [n_steps][4] = (NumErasuresPos of the step, num_blocks_err, num_erasures_exp, num_blocks_err_exp)."""
+    out = np.zeros((n_steps, 4), np.int64)
+    nb = ne = nbe = 0
+    for pos in range(n_steps):
+        q = pos - dv + 1
+        er = int(plain[q]) if q >= 0 else 0
+        nb += er > 0
+        q2 = pos - 2 * dv + 1
+        if q2 >= 0 and ex[q2] > 0:
+            ne += int(ex[q2]); nbe += 1
+        out[pos] = (er, nb, ne, nbe)
+    return out
+
+
 def peel_trajectory(vn_cn: np.ndarray, erased: np.ndarray, total_size: int, n_cn_all: int, num_steps: int,
                     picks: np.ndarray):
     """``orc_peel_trajectory`` (PD.py:705-789 with an injected pick sequence).  Returns (r1, recovered)."""

@@ -36,7 +36,10 @@ OUT = os.path.join(HERE, "_ref")
 REF_ROOT = os.environ.get("SCLDPC_REFERENCE_ROOT", "/root/reference")
 REF_DIR = os.path.join(REF_ROOT, "simulators_sc_ldpc", "bp_decoding")
 
+# "circ" is the "full" file with its `#undef CIRCULAR` line (BP_FULL.c:34) removed, i.e. the streaming / circular-buffer
+# build the reference ships compiled out: Def_nk = L*CNsPos, main -> main_streaming.
 SOURCES = {
+    "circ": "SC_LDPC_Simulator_BPDecoder_BEC_full_BP_LimIter_OlmosRandomEnsemble.c",
     "full": "SC_LDPC_Simulator_BPDecoder_BEC_full_BP_LimIter_OlmosRandomEnsemble.c",
     "sw": "SC_LDPC_Simulator_BPDecoder_BEC_SlidingWindow_LimIter_OlmosRandomEnsemble.c",
     "traj": "trajectories_SC_LDPC_Simulator_BPDecoder_BEC_full_BP_OlmosRandomEnsemble.c",
@@ -56,6 +59,7 @@ DEFAULT_SIZES = [
     (4, 8, 50, 5000),
     (4, 8, 100, 5000),
 ]
+CIRC_SIZES = [(4, 8, 16, 8), (4, 8, 24, 16), (3, 6, 16, 12)]      # ring length L, Def_M for the streaming decoder
 
 
 def so_name(variant: str, dv: int, dc: int, L: int, defM: int) -> str:
@@ -81,8 +85,10 @@ def build_one(variant: str, dv: int, dc: int, L: int, defM: int, force: bool = F
         "-e", rf"s/^#define Def_dc\s+[0-9]+/#define Def_dc {dc}/",
         "-e", rf"s/^#define Def_L\s+[0-9]+/#define Def_L {L}/",
         "-e", rf"s/^#define Def_M\s+[0-9]+/#define Def_M {defM}/",
-        src,
     ]
+    if variant == "circ":
+        sed += ["-e", r"/^#undef CIRCULAR/d"]
+    sed += [src]
     gcc = [
         os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-w", "-shared", "-fPIC", "-Dmain=ref_main",
         "-Wl,-Bsymbolic", "-x", "c", "-", "-o", out + ".tmp", "-lm",
@@ -105,6 +111,11 @@ def build_all(sizes=None, variants=("full", "sw", "traj"), verbose: bool = True)
     for (dv, dc, L, defM) in (sizes or DEFAULT_SIZES):
         for v in variants:
             outs.append(build_one(v, dv, dc, L, defM))
+            if verbose:
+                print(f"[oracle/_ref] {os.path.relpath(outs[-1], HERE)}")
+    if sizes is None:
+        for (dv, dc, L, defM) in CIRC_SIZES:
+            outs.append(build_one("circ", dv, dc, L, defM))
             if verbose:
                 print(f"[oracle/_ref] {os.path.relpath(outs[-1], HERE)}")
     return outs

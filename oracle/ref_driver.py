@@ -72,7 +72,7 @@ class RefLib:
             raise ValueError("the reference hard-codes VNs/position = 2*Def_M; only dc == 2*dv ensembles compile correctly")
         self.vns_pos = 2 * defM
         self.n = self.vns_pos * L
-        self.nk = (L + dv - 1) * defM
+        self.nk = L * defM if variant == "circ" else (L + dv - 1) * defM      # Def_nk under CIRCULAR (BP_FULL.c:36-40)
         self.lib = ctypes.CDLL(path)
         lib = self.lib
         self._VN = (ctypes.c_int * (self.n * (dv + 1))).in_dll(lib, "VNdegree")
@@ -176,6 +176,44 @@ class RefLib:
         res = self.lib.decodeBP_SW(*args)
         return dict(residual=int(res), erasures_p1=p1.value, blocks_err=nb.value, erasures_exp=ne.value,
                     blocks_err_exp=nbe.value, erased=self.VNerased.copy())
+
+
+    # ---- streaming / circular buffer (variant "circ") -------------------------------------------------
+    def stream_run(self, n_positions: int, W: int, eps: float, doped=()) -> dict:
+        """Drives the reference's streaming decoder exactly like main_streaming (BP_FULL.c:1991-2046) for n_positions
+        decode steps and returns, besides the per-step outputs, the UNROLLED chain it decoded: for every generated
+        absolute position p the VN->CN table (absolute CN ids (p+i)*CNsPos + local) and the channel values."""
+        assert self.variant == "circ"
+        lib, L, V, C, dv = self.lib, self.L, self.vns_pos, self.cns_pos, self.dv
+        ci = ctypes.c_int
+        darr = (ctypes.c_int * max(1, len(doped)))(*doped)
+        lib.initialize_arrays_circular(ci(self.n), ci(self.nk), ci(L), ci(C))
+        lag = L // 2
+        vn_cn, chan = [], []
+
+        def gen(p):
+            lib.generate_stream_pos(ci(p), ci(L), ctypes.c_double(eps), ci(V), ci(C), ci(len(doped)), darr)
+            lib.initialize_messages_circular(ci(p), ci(L), ci(V), ci(C))
+            pb = p % L
+            rows = self.VNdegree[pb * V:(pb + 1) * V, 1:].astype(np.int64)
+            # ring CN id -> absolute: edge i of a VN at absolute position p goes to absolute CN position p + i
+            local = rows % C
+            vn_cn.append(((p + np.arange(dv))[None, :] * C + local).astype(np.int32))
+            chan.append(self.LLRsChannel[pb * V:(pb + 1) * V].astype(np.uint8).copy())
+
+        for p in range(lag):
+            gen(p)
+        nb, ne, nbe = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        lib.decodeBP_SW_circular.restype = ctypes.c_int
+        steps = []
+        g = lag
+        for pos in range(n_positions):
+            er = lib.decodeBP_SW_circular(ci(pos), ci(self.n), ci(L), ci(W), ci(V), ci(C), ctypes.byref(nb), ctypes.byref(ne),
+                                          ctypes.byref(nbe))
+            steps.append((int(er), nb.value, ne.value, nbe.value))
+            gen(g)
+            g += 1
+        return dict(vn_cn=np.stack(vn_cn), chan=np.stack(chan), steps=np.array(steps, np.int64))
 
 
 _cache: dict = {}

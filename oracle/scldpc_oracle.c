@@ -186,6 +186,15 @@ static int expurgate_pos(const orc_state *s, const unsigned char *erased, int vn
     return exp_pos;
 }
 
+/* Per-position erasure counts and expurgated counts (get_deg_two_ss, BP_FULL.c:1227-1283) of a decided frame:
+ * plain[p] = erased VNs of position p, exp[p] = plain[p] - 2 * (accepted size-two stopping sets of position p). */
+void orc_position_counts(int n, int nk, int L, int vns_pos, int dv, int dc, const int *vn_cn, const int *cn_deg,
+                         const int *cn_vn, const unsigned char *erased, int *plain, int *exp_cnt)
+{
+    orc_state s = { n, nk, dv, dc, vn_cn, cn_deg, cn_vn, NULL, NULL, NULL, NULL, NULL };
+    for (int p = 0; p < L; p++) exp_cnt[p] = expurgate_pos(&s, erased, p, vns_pos, &plain[p]);
+}
+
 /* ------------------------------------------------------------------------------------------------- */
 /* decodeBP: full flooding BP (BP_FULL.c:900-1140, BP_TRAJ.c:901-1151)                                */
 /* ------------------------------------------------------------------------------------------------- */
