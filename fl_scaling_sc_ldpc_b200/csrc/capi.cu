@@ -17,6 +17,7 @@ int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, c
 void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_frames, cudaStream_t st);
 void bp_launch_window_begin(const BpParams &p, int n_frames, cudaStream_t st);
 void bp_launch_init_ctrl_only(const BpParams &p, int n_frames, cudaStream_t st);
+int bp_launch_window_persistent(int dv, int dc, const BpParams &p, int num_it, cudaStream_t st);
 int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
 int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
@@ -551,6 +552,10 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
     bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
     CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
     CU(cudaGetLastError());
+    // Opt-in (SCLDPC_PERSISTENT=1): measured on B200 the cooperative kernel is 15-25 % SLOWER than two launches per
+    // iteration (W=3: 81 vs 70 ms, W=10: 275 vs 215 ms for 4 graphs x 1024 frames, L=100, M=10000) -- three grid-wide
+    // syncs per iteration and 2 instead of 3-4 resident blocks per SM cost more than the launches they replace.
+    bool persistent = env_int("SCLDPC_PERSISTENT", 0, 0, 1) != 0;
     for (int posW = 0; posW < nwin && d->n_frames > 0; posW++) {
         long long c0 = (long long)posW * cp, c1 = c0 + (long long)W * cp;
         if (c1 > cn_clip) c1 = cn_clip;
@@ -570,7 +575,15 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
         p.win_edges = ce + (v1 - v0) * d->dv;
         bp_launch_window_begin(p, d->n_frames, st);
         const int NumIt = (square && posW == 0) ? cap0 : cap;      // BP_SW.c:699-702
-        if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr))) return rc;
+        // one cooperative launch per window (grid-wide syncs between the sweeps); two launches per iteration otherwise
+        p.max_it = NumIt;
+        p.row = -1;
+        int prc = persistent ? bp_launch_window_persistent(d->dv, d->dc, p, NumIt, st) : -2;
+        if (prc == -1) return fail(SCLDPC_EINVAL, "unsupported degrees");
+        if (prc == -2) {
+            persistent = false;
+            if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr))) return rc;
+        }
     }
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   1, square ? ms : 0, square ? W - 2 : W - 2 - ms};   // posW in [ms, W-2] (BP_SW.c:846-847)

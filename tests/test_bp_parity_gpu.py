@@ -99,8 +99,18 @@ def test_full_bp_extreme_channels():
         check_bp(eng.decode_bp_full(fb, 0, is_term, trajectory=True, max_rows=32), ref, rows=True)
 
 
+@pytest.fixture(params=["two_launches", "persistent"])
+def window_mode(request, monkeypatch):
+    """the window decoder as two launches per iteration (default) and as one cooperative launch per window"""
+    if request.param == "persistent":
+        monkeypatch.setenv("SCLDPC_PERSISTENT", "1")
+    else:
+        monkeypatch.delenv("SCLDPC_PERSISTENT", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("dv,dc,L,M", [(4, 8, 10, 50), (3, 6, 10, 48), (4, 8, 14, 64)])
-def test_window_bp_matches_oracle(dv, dc, L, M):
+def test_window_bp_matches_oracle(dv, dc, L, M, window_mode):
     eps = [0.35, 0.44, 0.47, 0.52] if dv != 3 else [0.3, 0.38, 0.42]
     graphs, chan, _ = util.random_case(dv, dc, L, M, G=2, F=40, eps_list=eps, seed=2000 + L + M, doped_every=7)
     fb = make_batch(dv, dc, L, M, graphs, chan)
