@@ -113,6 +113,8 @@ __device__ __forceinline__ void bp_cn_sweep_body(const BpParams &p, const int g)
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    // old messages are only needed for frames that hold a lane but are no longer iterating in this window
+    const bool need_old = FREEZE && neq(act, valid_chunk_mask(k, p.n_valid));
     const u128 *__restrict__ v2c = p.v2c + (size_t)g * (p.E + 1) * ch;
     u128 *__restrict__ c2v = p.c2v + (size_t)g * p.nk * DC * ch;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void bp_cn_sweep_body(const BpParams &p, const int g)
 #pragma unroll
             for (int j = DC - 1; j >= 0; j--) { out[j] |= acc; acc |= in[j]; }
             u128 *dst = c2v + ((size_t)c * DC) * ch + k;
-            if (FREEZE) {
+            if (FREEZE && need_old) {                           // some frame of this chunk has stopped: keep its messages
 #pragma unroll
                 for (int j = 0; j < DC; j++) out[j] = sel(act, out[j], dst[(size_t)j * ch]);
             }
@@ -250,6 +252,7 @@ __device__ __forceinline__ void bp_vn_sweep_body(const BpParams &p, const int g)
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const bool need_old = FREEZE && neq(act, valid_chunk_mask(k, p.n_valid));
     u128 acc_new = zero128(), acc_er = zero128();
 
     if (nz(act)) {
@@ -280,7 +283,7 @@ __device__ __forceinline__ void bp_vn_sweep_body(const BpParams &p, const int g)
 #pragma unroll
             for (int i = DV - 1; i >= 0; i--) { out[i] &= acc; acc &= in[i]; }
             u128 *dst = v2c + ((size_t)v * DV) * ch + k;
-            if (FREEZE) {
+            if (FREEZE && need_old) {
 #pragma unroll
                 for (int i = 0; i < DV; i++) out[i] = sel(act, out[i], dst[(size_t)i * ch]);
                 xn = sel(act, xn, xo);

@@ -188,6 +188,7 @@ static int setup_params(const scldpc_dims_t *d, const scldpc_batch_t *b, uint32_
     p->E = p->n * d->dv;
     p->L = d->L; p->vns_pos = d->vns_pos; p->cns_pos = d->cns_pos;
     p->G = d->n_graphs; p->W = d->n_words; p->chunks = d->n_words / 2; p->lanes = 64 * d->n_words;
+    p->n_valid = d->n_frames;
     p->chunk_shift = 0;
     while ((1 << p->chunk_shift) < p->chunks) p->chunk_shift++;
     p->vn_cn = b->vn_cn_dev; p->vn_slot = b->vn_slot_dev; p->cn_edge = b->cn_edge_dev;
@@ -457,6 +458,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     p.n = d->L * d->vns_pos; p.nk = (d->L + d->dv - 1) * d->cns_pos; p.E = p.n * d->dv;
     p.L = d->L; p.vns_pos = d->vns_pos; p.cns_pos = d->cns_pos;
     p.G = d->n_graphs; p.W = d->n_words; p.chunks = d->n_words / 2; p.lanes = 64 * d->n_words;
+    p.n_valid = d->n_frames;
     p.chunk_shift = 0;
     while ((1 << p.chunk_shift) < p.chunks) p.chunk_shift++;
     p.vn_cn = b->vn_cn_dev; p.vn_slot = b->vn_slot_dev; p.cn_edge = b->cn_edge_dev; p.chan = nullptr;

@@ -26,6 +26,14 @@ __device__ __forceinline__ u128 sel(u128 m, u128 a, u128 b) { return make_u128((
 __device__ __forceinline__ u128 zero128() { return make_u128(0ull, 0ull); }
 __device__ __forceinline__ u128 ones128() { return make_u128(~0ull, ~0ull); }
 
+// lanes of chunk k (128 lanes) that hold a frame when n_valid frames are in use
+__device__ __forceinline__ u128 valid_chunk_mask(int k, int n_valid)
+{
+    const int lo = k * 128;
+    auto w = [&](int base) -> u64 { return n_valid >= base + 64 ? ~0ull : (n_valid <= base ? 0ull : ((1ull << (n_valid - base)) - 1ull)); };
+    return make_u128(w(lo), w(lo + 64));
+}
+
 // streaming (read-once) global load through the non-coherent path, no L1 allocation
 __device__ __forceinline__ u128 ld_stream(const u128 *p)
 {
@@ -172,6 +180,7 @@ __device__ __forceinline__ void load_row(const int32_t *row, int (&e)[D])
 struct BpParams {
     // dimensions
     int dv, dc, n, nk, E, L, vns_pos, cns_pos, G, W, chunks, chunk_shift, lanes;
+    int n_valid;              // frames per graph (lanes >= n_valid never hold a frame)
     // graph + channel
     const int32_t *vn_cn;     // [G][n][dv]
     const int32_t *vn_slot;   // [G][n][dv]
