@@ -303,17 +303,21 @@ def run_ours(args):
         fi_per_launch = local_frame_iters / max(1, n_iter_launches)
         cn_bytes = fi_per_launch * (2 * E_EDGES) / 8.0
         vn_bytes = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
-        traffic = None
+        traffic = traffic_note = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
             try:
-                traffic = json.load(open(tpath)).get("vn_sweep_dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("vn_sweep_dram_bytes_per_launch")
+                traffic_note = ("ncu --set full capture of one launch with %d graph(s) decoding (%s); the average launch of "
+                                "the timed region carries %.0f active frames" % (tj.get("graphs_decoding_in_captured_launch", 1),
+                                                                               tj.get("algorithmic_bytes_same_launch", ""), fi_per_launch))
             except Exception:
                 traffic = None
         vn_name = "bp_vn_stream_kernel<4>" if stream_mode else "bp_vn_wave_kernel<4,false>"
         ach = vn_bytes / vn_avg / 1e9
         roof = {"bound": "hbm", "kernel": vn_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "launches_sampled": n_s, "avg_launch_ms": 1e3 * vn_avg,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "launches_sampled": n_s, "avg_launch_ms": 1e3 * vn_avg,
                 "frame_iterations_per_launch": fi_per_launch,
                 "algorithmic_bytes": "(2E+n)/8 B per useful frame-iteration (reads E c2v bits + n channel bits, writes E v2c bits)"}
         ach_c = cn_bytes / cn_avg / 1e9
