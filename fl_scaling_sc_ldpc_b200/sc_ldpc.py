@@ -49,3 +49,13 @@ def gen_slots_tail_biting(l, r, L, M):
 def gen_vn_indices(l, r, L, M):
     """[L][l][M] view of ``gen_slots`` (SC.py:33-38)."""
     return np.ascontiguousarray(gen_slots(l, r, L, M).reshape(L, M, l).transpose(0, 2, 1))
+
+
+def gen_vn_indices_tail_biting(l, r, L, M):
+    """[L][l][M] view of ``gen_slots_tail_biting`` (SC.py:41-45)."""
+    return np.ascontiguousarray(gen_slots_tail_biting(l, r, L, M).reshape(L, M, l).transpose(0, 2, 1))
+
+
+def vn_indices_to_transmissions(vn_indices, l, L, M):
+    """SC.py:48-50: [L][l][M] -> [L*M][l]."""
+    return np.ascontiguousarray(np.asarray(vn_indices).transpose(0, 2, 1).reshape(L * M, l))

@@ -160,6 +160,21 @@ def test_generated_ensemble_is_valid_and_uniformish():
     assert len(set(firsts.tolist())) > 15 and firsts.max() < cns
 
 
+def test_ensemble_module_drop_ins():
+    from fl_scaling_sc_ldpc_b200 import sc_ldpc as scx, sc_ldpc_protograph as spx
+    scx.set_seed(3)
+    vi = scx.gen_vn_indices(3, 6, 5, 12)
+    assert vi.shape == (5, 3, 12)
+    tr = scx.vn_indices_to_transmissions(vi, 3, 5, 12)
+    assert tr.shape == (60, 3) and (tr[:12, 0] // 6 == 0).all()
+    assert scx.gen_vn_indices_tail_biting(3, 6, 5, 12).shape == (5, 3, 12)
+    g = spx.gen_slots_from_position(4, 8, 24)                                # sc_ldpc_protograph.py:17
+    assert g.shape == (24, 4)
+    for portion in range(2):
+        for i in range(4):
+            assert sorted(g[portion * 12:(portion + 1) * 12, i].tolist()) == list(range(i * 12, (i + 1) * 12))
+
+
 def test_generated_protograph_ensemble_is_valid():
     """sc_ldpc_protograph.gen_slots_from_position: per (position, portion, edge type) a permutation of the position's CNs"""
     l, r, L, M = 4, 8, 7, 48
