@@ -63,3 +63,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "scldpc_oracle" not in src, f
+
+
+def test_header_is_plain_c_and_a_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """the drop-in boundary from C: include/scldpc.h compiles as C11, examples/decode_host.c links against the library,
+    and -- on a box without a GPU -- the call returns the library's error instead of computing anything on the CPU"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "fl_scaling_sc_ldpc_b200")
+    hdr_check = tmp_path / "hdr.c"
+    hdr_check.write_text('#include "scldpc.h"\nint main(void) { return scldpc_version() < 0; }\n')
+    exe = tmp_path / "decode_host"
+    for src, out in ((str(hdr_check), str(tmp_path / "hdr")), (os.path.join(ROOT, "examples", "decode_host.c"), str(exe))):
+        r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", src, "-I", inc, "-L", libdir, "-lscldpc",
+                            "-Wl,-rpath," + libdir, "-o", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    if _lib.lib().scldpc_device_count() == 0:
+        assert r.returncode == 2 and "no CUDA device" in r.stderr
+    else:
+        assert r.returncode == 0 and r.stdout.startswith("frames 16")

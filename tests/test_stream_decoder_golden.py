@@ -40,3 +40,23 @@ def test_doped_positions_are_known_in_the_reference_stream():
         if doped:
             assert not chan[p].any()
     assert chan[[p for p in range(chan.shape[0]) if p % 10 not in (5, 7, 9)]].any()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_stream_counters_match_the_reference(name):
+    """host logic of fl_scaling_sc_ldpc_b200.streaming (counters, periodic doping, bits / blocks generated) fed with the
+    oracle's per-position counts"""
+    from fl_scaling_sc_ldpc_b200 import streaming
+    dv, dc, L, defM, W, steps, vn_cn, chan, ref = case(name)
+    npos, V = vn_cn.shape[0], vn_cn.shape[1]
+    g = oracle.Graph(vn_cn.reshape(-1, dv), npos, V, defM, dv, dc)
+    o = oracle.decode_bp_sw(g, chan.reshape(-1).astype(np.int32), W, 10 ** 9, 0, square=0, is_term=1)
+    plain, ex = oracle.position_counts(g, o["erased"])
+    doped = list(Z[name + "_doped"])
+    c = streaming.stream_counters(plain, ex, steps, dv, doped, V)
+    got = np.stack([c["erasures_pos"], c["num_blocks_err"], c["num_erasures_exp"], c["num_blocks_err_exp"]], axis=1)
+    assert (got == ref).all()
+    # main_streaming's generated-bit accounting (BP_FULL.c:2017-2026)
+    nb = sum(1 for pos in range(steps) if pos - dv + 1 >= 0 and not streaming.is_position_doped_streaming(pos - dv + 1, doped))
+    assert c["num_blocks_generated"][-1] == nb and c["num_bits_generated"][-1] == nb * V
+    assert (c["num_erasures"] == np.cumsum(ref[:, 0])).all()
