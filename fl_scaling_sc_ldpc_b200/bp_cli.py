@@ -115,45 +115,57 @@ def run(prog: str, argv=None) -> int:
         name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_%dinit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, init_it, a.index)
     else:
         name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, a.index)
+    from . import dist as D
+    rank, world = D.init_from_env()
     graph_id = 0
+    sw = prog == "sw_lim_iter"
     for sim in range(a.points):
         eps = a.eps_ini - sim * a.eps_delta                            # inizio_sim, BP_FULL.c:300
         c = new_counters()
         f = 0
         traj_f = None
-        if prog == "bp_traj":
+        if prog == "bp_traj" and rank == 0:
             tname = "trajectories_%.4f_%s_SC_LDPC_%d_%d_L%d_M%d_BP_Full_%dit_Random_BLER_%d.dat" % (
                 eps, "terminated" if a.is_term else "truncated", a.dv, a.dc, a.L, a.M, a.max_it, a.index)
             traj_f = open(os.path.join(a.outdir, tname), "w")
         stop = False
+        # One round = world_size batches of G graphs (rank r decodes the r-th; graph and frame ids are global).  The
+        # per-frame results are all-gathered and every rank replays plr_computation / willIstop over them in frame order,
+        # so the files are the same for any number of GPUs.
+        rnd = 0
         while f < a.max_frames and not stop:
+            gid = graph_id + (rnd * world + rank) * G
+            rnd += 1
             fb = engine.FrameBatch(ens, G, fpg, nw)
-            fb.generate_graphs(seed, first_graph_id=graph_id)
-            fb.generate_erasures(eps, seed + 1, first_graph_id=graph_id, doping_points=doped)
-            graph_id += G
-            if prog == "sw_lim_iter":
+            fb.generate_graphs(seed, first_graph_id=gid)
+            fb.generate_erasures(eps, seed + 1, first_graph_id=gid, doping_points=doped)
+            if sw:
                 r = engine.decode_bp_window(fb, a.W, max_it, max(1, init_it), square=True, is_term=True)
             elif prog == "bp_traj":
                 r = engine.decode_bp_full(fb, max_it, is_term=bool(a.is_term), trajectory=True, max_rows=max_it)
             else:
                 r = engine.decode_bp_full(fb, max_it, is_term=True)
-            for g in range(G):
-                for k in range(fpg):
-                    if f >= a.max_frames or stop:
-                        break
-                    if traj_f is not None:
-                        traj_f.write(trajectory_text(r.rows[g, k], int(r.iters[g, k])))
-                    account(c, r.residual[g, k], r.blocks_err[g, k], r.erasures_exp[g, k], r.blocks_err_exp[g, k],
-                            r.erasures_p1[g, k] if prog == "sw_lim_iter" else 0)
-                    f += 1
-                    if c["frame_err"] >= a.min_frame_err:              # willIstop, BP_FULL.c:440-451
-                        stop = True
+            rec = np.stack([r.residual, r.blocks_err, r.erasures_exp, r.blocks_err_exp,
+                            r.erasures_p1 if sw else np.zeros_like(r.residual), r.iters], axis=-1).astype(np.int64)
+            rec = D.allgather_rows(rec).reshape(-1, 6)                 # [world*G*fpg], global frame order
+            rows = D.allgather_rows(r.rows).reshape((-1,) + r.rows.shape[2:]) if prog == "bp_traj" else None
+            for k in range(len(rec)):
+                if f >= a.max_frames or stop:
+                    break
+                if traj_f is not None:
+                    traj_f.write(trajectory_text(rows[k], int(rec[k, 5])))
+                account(c, rec[k, 0], rec[k, 1], rec[k, 2], rec[k, 3], rec[k, 4])
+                f += 1
+                if c["frame_err"] >= a.min_frame_err:                  # willIstop, BP_FULL.c:440-451
+                    stop = True
+        graph_id += (f + G * fpg - 1) // (G * fpg) * G                 # the batches a single process would have drawn
         if traj_f is not None:
             traj_f.close()
-        with open(os.path.join(a.outdir, name), "w" if sim == 0 else "a") as out:
-            if sim == 0:
-                out.write(HEADER)
-            out.write(result_row(eps, ens.n, a.L, f, c))
+        if rank == 0:
+            with open(os.path.join(a.outdir, name), "w" if sim == 0 else "a") as out:
+                if sim == 0:
+                    out.write(HEADER)
+                out.write(result_row(eps, ens.n, a.L, f, c))
     return 0
 
 

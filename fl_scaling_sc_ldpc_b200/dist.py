@@ -17,6 +17,31 @@ def world():
     return 0, 1
 
 
+def init_from_env() -> tuple[int, int]:
+    """Joins the job ``torchrun`` (or any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*) started: one
+    process per GPU, NCCL when CUDA is there, gloo otherwise.  A plain ``python ...`` launch stays single-process."""
+    import os
+    if dist.is_initialized() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return world()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    backend = os.environ.get("SCLDPC_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)      # gloo: ranks may share a GPU (tests on a one-GPU box); collectives go through the host
+    return world()
+
+
+def shutdown():
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def shard_graph_ids(first: int, count: int, rank: int | None = None, world_size: int | None = None):
     """Graph ids [first, first+count) are dealt round-robin in blocks: rank r gets ids first + r, first + r + N, ...
     Ids are global, so the union of all ranks' realisations does not depend on N."""
@@ -42,6 +67,37 @@ def allreduce_max(value: float, device=None) -> float:
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _comm_device():
+    """device the collectives run on: the current GPU under NCCL, the CPU under gloo"""
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def allgather_rows(arr: np.ndarray) -> np.ndarray:
+    """All ranks contribute an array of the same shape; returns them stacked as [world][...] (identical on every rank)."""
+    arr = np.ascontiguousarray(arr)
+    n = world()[1]
+    if n == 1:
+        return arr[None]
+    t = torch.as_tensor(arr).to(_comm_device())
+    out = [torch.empty_like(t) for _ in range(n)]
+    dist.all_gather(out, t)
+    return np.stack([o.cpu().numpy() for o in out])
+
+
+def allgather_tensor(t: torch.Tensor) -> torch.Tensor:
+    """Same for a tensor that stays where it is (device tensors under NCCL): returns [world][...]."""
+    n = world()[1]
+    if n == 1:
+        return t[None]
+    home = t.device
+    t = t.contiguous().to(_comm_device())
+    out = [torch.empty_like(t) for _ in range(n)]
+    dist.all_gather(out, t)
+    return torch.stack(out).to(home)
 
 
 def sequential_stop_index(fail_flags_local: np.ndarray, frame_ids_local: np.ndarray, threshold: int, device=None) -> int:

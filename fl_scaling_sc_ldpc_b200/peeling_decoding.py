@@ -20,6 +20,7 @@ the two protograph combinations that are broken upstream (soft doping, tail-biti
 from __future__ import annotations
 
 import ctypes
+import os
 import pickle
 import sys
 
@@ -110,7 +111,8 @@ def _peel_geometry(e, l_deg, r_deg, L, M, is_terminated):
 
 
 def simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_protograph, num_repeats=None, doping_points=[],
-                                  *, seed=None, frames_per_graph=1, first_frame=0, max_batch_frames=None, device_r1=False):
+                                  *, seed=None, frames_per_graph=1, first_frame=0, max_batch_frames=None, device_r1=False,
+                                  _local=False):
     """PD.py:705-789.  Returns ``(None, r1, plrs)``: ``r1`` int64 [num_repeats][num_pd_steps+1] with the number of
     degree-one CNs after every peeling step, ``plrs`` float64 [num_repeats] the fraction of VNs left erased.
 
@@ -118,6 +120,31 @@ def simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_proto
     _check_ensemble(is_protograph, doping_points)
     if not num_repeats:
         num_repeats = 100
+    from . import dist as D
+    rank, world = D.world()
+    if world > 1 and not _local:
+        # every rank peels a contiguous range of the frames (frame ids are global) and the results are all-gathered
+        q = (num_repeats + world - 1) // world
+        lo, hi = min(rank * q, num_repeats), min((rank + 1) * q, num_repeats)
+        cols = _peel_geometry(e, l_deg, r_deg, L, M, is_terminated)[3] + 1
+        if hi > lo:
+            _, r1_l, plrs_l = simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_protograph, hi - lo, doping_points,
+                                                            seed=seed, frames_per_graph=frames_per_graph, first_frame=first_frame + lo,
+                                                            max_batch_frames=max_batch_frames, device_r1=True, _local=True)
+            r1_l = torch.cat(r1_l, dim=0)
+        else:
+            r1_l, plrs_l = torch.zeros((0, cols), dtype=torch.int32, device=engine._device()), np.zeros(0)
+        pad = torch.zeros((q, cols), dtype=torch.int32, device=r1_l.device)
+        pad[: hi - lo] = r1_l
+        pl = np.zeros(q)
+        pl[: hi - lo] = plrs_l
+        r1_all = D.allgather_tensor(pad)                                 # [world][q][cols]
+        plrs = D.allgather_rows(pl).reshape(-1)
+        r1_all = r1_all.reshape(world * q, cols)[:num_repeats]         # rank r filled rows [r*q, r*q + its count): contiguous
+        plrs = plrs[:num_repeats]
+        if device_r1:
+            return None, [r1_all], plrs
+        return None, r1_all.cpu().numpy().astype("int"), plrs
     seed = _state["seed"] if seed is None else seed
     cns_per_pos, num_positions, total_size, num_pd_steps = _peel_geometry(e, l_deg, r_deg, L, M, is_terminated)
     ens = engine.Ensemble(l_deg, r_deg, L, M)
@@ -183,7 +210,7 @@ def account_lost(lost: np.ndarray, transmissions: np.ndarray, M: int):
     lost_exp = set()
     for s in big:
         lost_exp |= {int(v) // M for v in lost[s]}              # int(birthday / cns_per_pos) = VN position
-    return len(lost), len(big) > 0, sum(len(s) for s in big), len(lost_exp)
+    return len(lost), int(len(big) > 0), sum(len(s) for s in big), len(lost_exp)
 
 
 def counted_positions(l, L, num_positions, ignored_head, ignored_tail, is_tail_biting=False) -> np.ndarray:
@@ -198,7 +225,7 @@ def counted_positions(l, L, num_positions, ignored_head, ignored_tail, is_tail_b
 
 def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is_tail_biting, num_repeats=int(1e5),
                      max_fuckups=2000, doping_points=[], *, seed=None, frames_per_graph=128, graphs_per_batch=8, first_frame=0,
-                     progress=True, _batch_factory=None):
+                     progress=True, _batch_factory=None, _records_fn=None):
     """PD.py:591-701.  Returns the reference's 13-tuple
     ``(FER, FER_exp, PLR, PLR_exp, n_frames_failed_exp, n_frames, n_vn_failed_exp, n_vn_generated, failures, gens,
     n_blocks_failed_exp, n_blocks_generated, BLER_exp)``.
@@ -231,16 +258,23 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
     counted = counted_positions(l, L, num_positions, ignored_head, ignored_tail, bool(is_tail_biting))
     pos_mask = torch.as_tensor(np.repeat(counted, M))
 
+    from . import dist as D
+    rank, world = D.world()
     num_fuckups = num_fuckups_truncated = 0
     total_generated = total_failed = total_failed_expurgated = 0
     total_blocks_generated = total_blocks_failed_exp = 0
     o = -1
-    prog = _Progress(num_repeats, progress)
+    prog = _Progress(num_repeats, progress and rank == 0)
     stop = False
-    while o + 1 < num_repeats and not stop:
-        left = num_repeats - (o + 1)
-        G = min(graphs_per_batch, (left + fpg - 1) // fpg)
-        gid0 = (first_frame + o + 1) // fpg
+    unscanned = ignored_head_schedule * cns_per_pos
+
+    def decode_records(G, gid0):
+        """decodes G graphs x fpg frames; one row (num_lost, big, lost_exp, blocks_exp) per frame, in frame order"""
+        rec = np.zeros((G * fpg, 4), np.int64)
+        if G == 0:
+            return rec
+        if _records_fn is not None:                                      # CPU tests of the round / gather / replay logic
+            return np.asarray(_records_fn(G, fpg, gid0), np.int64).reshape(G * fpg, 4)
         if _batch_factory is not None:                                   # tests inject codes and erasure masks here
             fb = _batch_factory(ens, G, fpg, gid0)
         else:
@@ -250,42 +284,56 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
         # non-terminated: the decoder never uses CNs >= total_size (truncated BP, BP_TRAJ.c:944-948 semantics).
         # unbounded: slots below ignored_head_schedule*cns_per_pos are never scanned (PD.py:656), they only decode
         # when a removal leaves them with one user -- scldpc_bp_set_unscanned_head
-        _lib.check(_lib.lib().scldpc_bp_set_unscanned_head(ignored_head_schedule * cns_per_pos))
+        _lib.check(_lib.lib().scldpc_bp_set_unscanned_head(unscanned))
         try:
             res = engine.decode_bp_full(fb, engine.UNLIMITED, is_term=bool(is_terminated) and not is_tail_biting)
         finally:
             _lib.lib().scldpc_bp_set_unscanned_head(0)
         words = res.erased_words                                         # [G][n][W] on the device
-        transmissions = None
         for g in range(G):
-            if stop:
-                break
             tr_g = None
-            for f in range(fpg):
-                if o + 1 >= num_repeats:
-                    stop = True
-                    break
-                o += 1
-                total_generated += curr_generated
-                total_blocks_generated += blocks_per_frame
-                num_lost = 0
-                if res.residual[g, f] > 0:
-                    bits = ((words[g, :, f >> 6] >> (f & 63)) & 1).bool().cpu() & pos_mask
-                    lost = torch.nonzero(bits).reshape(-1).numpy()
-                    num_lost = len(lost)
-                    if num_lost >= 1:
-                        if tr_g is None:
-                            tr_g = fb.vn_cn[g].cpu().numpy()
-                        _, big, lost_e, blocks_e = account_lost(lost, tr_g, M)
-                        num_fuckups += 1
-                        total_failed += num_lost
-                        num_fuckups_truncated += int(big)
-                        total_failed_expurgated += lost_e
-                        total_blocks_failed_exp += blocks_e
-                if num_fuckups >= max_fuckups:
-                    stop = True
-                    break
-        prog.update(G * fpg, "FER: %.5f (%.5f); PLR: %.5f (%.5f); BLER: %.5f" % (
+            for f in np.flatnonzero(res.residual[g] > 0):
+                f = int(f)
+                bits = ((words[g, :, f >> 6] >> (f & 63)) & 1).bool().cpu() & pos_mask
+                lost = torch.nonzero(bits).reshape(-1).numpy()
+                if len(lost) >= 1:
+                    if tr_g is None:
+                        tr_g = fb.vn_cn[g].cpu().numpy()
+                    rec[g * fpg + f] = account_lost(lost, tr_g, M)
+        return rec
+
+    # Frames are decoded in rounds of world_size x graphs_per_batch graphs (rank r takes the r-th batch of the round; graph
+    # ids are global), the per-frame records are all-gathered, and every rank then walks the frames in global order with
+    # the reference's sequential bookkeeping -- so the result, including the max_fuckups cut (PD.py:698), is the same for
+    # any number of GPUs.
+    while o + 1 < num_repeats and not stop:
+        left = num_repeats - (o + 1)
+        graphs_left = (left + fpg - 1) // fpg
+        gid_round = (first_frame + o + 1) // fpg
+        G_r = max(0, min(graphs_per_batch, graphs_left - rank * graphs_per_batch))
+        rec = decode_records(G_r, gid_round + rank * graphs_per_batch)
+        pad = np.full((graphs_per_batch * fpg, 4), -1, np.int64)
+        pad[: len(rec)] = rec
+        allrec = D.allgather_rows(pad).reshape(-1, 4)
+        for row in allrec:
+            if row[0] < 0:
+                continue
+            if o + 1 >= num_repeats:
+                stop = True
+                break
+            o += 1
+            total_generated += curr_generated
+            total_blocks_generated += blocks_per_frame
+            if row[0] >= 1:
+                num_fuckups += 1
+                total_failed += int(row[0])
+                num_fuckups_truncated += int(row[1])
+                total_failed_expurgated += int(row[2])
+                total_blocks_failed_exp += int(row[3])
+            if num_fuckups >= max_fuckups:
+                stop = True
+                break
+        prog.update(min(left, world * graphs_per_batch * fpg), "FER: %.5f (%.5f); PLR: %.5f (%.5f); BLER: %.5f" % (
             num_fuckups / (o + 1), num_fuckups_truncated / (o + 1), total_failed / max(1, total_generated),
             total_failed_expurgated / max(1, total_generated), total_blocks_failed_exp / max(1, total_blocks_generated)))
     prog.close()
@@ -336,6 +384,8 @@ def main_simulate_variance(argv=None):
     num_runs = int(argv[9]); num_runs_batch = int(argv[10]); ftheory = argv[11]
     with open(ftheory, 'rb') as f:
         r1s_theory = pickle.load(f)[0]
+    from . import dist as D
+    rank, _world = D.init_from_env()          # under torchrun the frames of every chunk are split over the GPUs
     isfirst = True
     ssquares, counts = None, None
     num_rounds = int(num_runs / num_runs_batch)
@@ -346,8 +396,9 @@ def main_simulate_variance(argv=None):
         ssquares = ssquares_chunk if isfirst else ssquares + ssquares_chunk
         counts = counts_chunk if isfirst else counts + counts_chunk
         isfirst = False
-    with open(fname, 'wb') as f:
-        pickle.dump((ssquares, counts), f)
+    if rank == 0:
+        with open(fname, 'wb') as f:
+            pickle.dump((ssquares, counts), f)
     return ssquares, counts
 
 
@@ -366,14 +417,18 @@ def main_simulate_sc_ldpc(argv=None):
     L += len(doping_points)                                         # PD.py:1343
     hdr = (f"# SC-LDPC ({l},{r},L={L},M={M}) terminated:{is_terminated}, proto:{is_protograph}, bounded:{is_bounded}, "
            f"tail biting:{is_tail_biting}. num_repeats={num_repeats}, max_fuckups={max_fuckups}, doping_points={doping_points}.")
-    with open(fname, 'wt') as f:
-        print(hdr)
+    from . import dist as D
+    rank, _world = D.init_from_env()          # under torchrun every round of batches is spread over the GPUs
+    with open(fname if rank == 0 else os.devnull, 'wt') as f:
+        if rank == 0:
+            print(hdr)
         print(hdr, file=f)
         f.flush()
         for e in es:
             ber, ber_truncated, plr, plr_exp, fbl, tbl, fbit, tgen, _flrs, _gens, fblocks, tblocks, bler = simulate_sc_ldpc(
                 e, l, r, L, M, is_terminated, is_protograph, is_bounded, is_tail_biting, num_repeats, max_fuckups, doping_points)
             print(e, ber, ber_truncated, plr, plr_exp, fbl, tbl, fbit, tgen, fblocks, tblocks, bler, file=f)
-            print(e, ber, ber_truncated, plr, plr_exp, fbl, tbl, fbit, tgen, fblocks, tblocks, bler)
+            if rank == 0:
+                print(e, ber, ber_truncated, plr, plr_exp, fbl, tbl, fbit, tgen, fblocks, tblocks, bler)
             f.flush()
             sys.stdout.flush()

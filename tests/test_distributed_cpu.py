@@ -63,3 +63,56 @@ def test_single_process_fallbacks():
     assert D.allreduce_counters([1, 2]).tolist() == [1, 2] and D.allreduce_max(3.5) == 3.5
     assert D.sequential_stop_index(np.array([0, 1, 0, 1, 1]), np.arange(5), 2) == 4
     assert D.sequential_stop_index(np.array([0, 1]), np.arange(2), 2) == -1
+
+
+# ---- the drop-in drivers' rounds: world_size batches per round, all-gathered per-frame records, sequential replay ----------------
+def _fake_records(G, fpg, gid0):
+    """deterministic per-frame records from global ids only: (num_lost, big, lost_exp, blocks_exp)"""
+    rec = np.zeros((G * fpg, 4), np.int64)
+    for g in range(G):
+        for f in range(fpg):
+            k = (gid0 + g) * fpg + f
+            if (k * 2654435761 >> 7) % 9 == 0:
+                rec[g * fpg + f] = (3 + k % 5, int(k % 3 != 0), (2 + k % 4) * int(k % 3 != 0), 1 + k % 2 if k % 3 else 0)
+    return rec
+
+
+def _driver_args(num_repeats, max_fuckups):
+    return dict(e=0.45, l=4, r=8, L=12, M=64, is_terminated=True, is_protograph=False, is_bounded=True, is_tail_biting=False,
+                num_repeats=num_repeats, max_fuckups=max_fuckups, frames_per_graph=4, graphs_per_batch=3, first_frame=24,
+                progress=False, _records_fn=_fake_records)
+
+
+def _driver_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from fl_scaling_sc_ldpc_b200 import peeling_decoding as pdx
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for nr, mf in ((1000, 7), (50, 10 ** 6), (61, 3)):
+        t = pdx.simulate_sc_ldpc(**_driver_args(nr, mf))
+        out.append([float(x) for i, x in enumerate(t) if i not in (8, 9)])
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_simulate_sc_ldpc_rounds_match_single_process():
+    from fl_scaling_sc_ldpc_b200 import peeling_decoding as pdx
+    expect = []
+    for nr, mf in ((1000, 7), (50, 10 ** 6), (61, 3)):
+        t = pdx.simulate_sc_ldpc(**_driver_args(nr, mf))
+        expect.append([float(x) for i, x in enumerate(t) if i not in (8, 9)])
+    assert expect[0][4] <= 7 and expect[1][5] == 50                     # the cut fired / the frame budget was used up
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_driver_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert out == expect
