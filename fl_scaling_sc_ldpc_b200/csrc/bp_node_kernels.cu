@@ -1,0 +1,236 @@
+// bp_node_kernels.cu -- frame streams in the node-state formulation of flooding BP on the BEC (sm_100a).
+//
+// From the all-erased start the messages of flooding BP on the BEC are monotone, and the a-posteriori erased set after
+// iteration t is a function of the erased set after iteration t-1 alone ("parallel peeling"):
+//
+//     x_v(t) = x_v(t-1)  AND  for every CN c of v:  c has at least two erased neighbours in x(t-1)
+//
+// (a CN with exactly one erased neighbour resolves it; an extrinsic message that the message-passing decoder would still
+// hold back can only concern a VN that is already known).  The erased set -- hence the residual
+// erasures, the per-frame iteration count under the reference's stall rule (NumErasures == NumErasuresPrec,
+// BP_FULL.c:1046-1066), the error counts and the expurgation inputs -- is bit-identical to decodeBP's at every iteration;
+// tests/test_node_state_gpu.py holds it against the message kernels and the compiled reference.  What the formulation does
+// not carry are the messages themselves, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) and the window decoders
+// stay on the message kernels (bp_kernels.cu / bp_wave_kernels.cu), which remain the implementation of record.
+//
+// State per graph: x [n][chunks] (1 bit per VN and frame) and two [nk][chunks] ("this CN has >= 2 erased neighbours").
+//   CN sweep: gathers the dc x rows of a CN, writes its `two` row             (reads  E rows through L2, writes nk rows)
+//   VN sweep: x_v &= AND of the dv `two` rows of v; arms freed lanes with a new channel draw (reads E rows through L2)
+// Both gathers stay inside a band of dv positions (5 MB of x, 2.5 MB of `two` at M = 10000, 1024 frames), which lives in
+// L2; HBM only sees the sequential x / two / index streams: (2n + nk)/8 bytes per frame-iteration instead of (4E + n)/8.
+//
+// Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
+#include "common.cuh"
+
+namespace scldpc {
+
+// ------------------------------------------------------------------------------------------------------------
+// check-node sweep: two[c] = "at least two of the neighbours of c are erased"
+// ------------------------------------------------------------------------------------------------------------
+template <int DV, int DC>
+__global__ void __launch_bounds__(256, 5) ns_cn_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    if (!nz(act)) return;                                       // a thread keeps its chunk: blockDim and the stride are multiples of ch
+    const u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u128 *__restrict__ two = p.two + (size_t)g * p.nk * ch;
+    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept: two = 1
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+        const int c = idx >> p.chunk_shift;
+        int e[DC];
+        load_row<DC>(cn_edge + (size_t)c * DC, e);
+        u128 in[DC];
+#pragma unroll
+        for (int j = 0; j < DC; j++) in[j] = (e[j] != p.E) ? ld_stream(x + (size_t)(e[j] / DV) * ch + k) : zero128();
+        u128 one = zero128(), tw = zero128();
+#pragma unroll
+        for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
+        two[(size_t)c * ch + k] = tw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// variable-node sweep + end of the iteration (last block): same control flow as bp_vn_stream_kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int DV, bool ARM>
+__global__ void __launch_bounds__(256, 4) ns_vn_kernel(BpParams p)
+{
+    // the CN sweep walks graphs and nodes upwards, this one downwards: each sweep starts on what the other touched last
+    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
+    __shared__ int s_last;
+    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_new[threadIdx.x] = 0; s_er[threadIdx.x] = 0; s_first[threadIdx.x] = 0; }
+    __syncthreads();
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const u128 arm = ARM ? reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k] : zero128();
+    const bool lane_work = nz(act | arm);
+    u128 acc_new = zero128(), acc_er = zero128(), acc_first = zero128();
+    const u128 *__restrict__ two = p.two + (size_t)g * p.nk * ch;
+    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    const int32_t *__restrict__ vn_cn = p.vn_cn + (size_t)g * p.n * DV;
+    const int items = p.n << p.chunk_shift;
+    const int stride = gridDim.x * blockDim.x;
+    const u64 thr = (ARM && nz(arm)) ? p.thr[g] : 0ull;
+    const uint64_t gid = p.first_graph + (uint64_t)g;
+    if (lane_work)
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+            const int v = p.vn_reverse ? p.n - 1 - (idx >> p.chunk_shift) : (idx >> p.chunk_shift);
+            int c[DV];
+            load_row<DV>(vn_cn + (size_t)v * DV, c);
+            u128 t = ld_stream(two + (size_t)c[0] * ch + k);
+#pragma unroll
+            for (int i = 1; i < DV; i++) t &= ld_stream(two + (size_t)c[i] * ch + k);
+            const u128 xo = x[(size_t)v * ch + k];
+            // a stopped frame sits at a fixed point of the rule, so lanes outside `act` need no mask
+            u128 xn = xo & t;
+            if (ARM && nz(arm)) {
+                // new frames: the erased set starts as the channel's (Lji = channel value on every edge, BP_FULL.c:913-917)
+                const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
+                u128 cw = zero128();
+                // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
+                // usually shared by up to four armed lanes
+                uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
+                for (int half = 0; half < 2; half++) {
+                    u64 m = half ? arm.y : arm.x, w = 0;
+                    while (m && !forced) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
+                        if ((fr >> 2) != blk) {
+                            blk = fr >> 2;
+                            philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
+                                          (uint32_t)(p.seed >> 32), r4);
+                        }
+                        if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
+                    }
+                    if (half) cw.y = w; else cw.x = w;
+                }
+                xn = sel(arm, cw, xn);
+                acc_first |= ~cw & arm;                         // NumErasuresPrec = n before the first iteration: it makes
+            }                                                   // "progress" iff the channel left some VN known
+            if (neq(xn, xo)) x[(size_t)v * ch + k] = xn;
+            acc_new |= xo & ~xn & act;
+            acc_er |= xn & act;
+        }
+    acc_new = warp_or_same_chunk(acc_new, ch);
+    acc_er = warp_or_same_chunk(acc_er, ch);
+    if (ARM) acc_first = warp_or_same_chunk(acc_first, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
+        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
+        if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
+        if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
+        if (ARM) {
+            if (acc_first.x) atomicOr(&s_first[2 * k], acc_first.x);
+            if (acc_first.y) atomicOr(&s_first[2 * k + 1], acc_first.y);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
+        if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
+        if (ARM && (s_first[w] & ~ld_cg(p.first_new + g * p.W + w))) atomicOr(p.first_new + g * p.W + w, s_first[w]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- end of the iteration for graph g ----
+    __shared__ u64 s_act[SCLDPC_MAX_WORDS];
+    const int W = p.W;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        const u64 er = ld_cg(p.any_er + g * W + w);
+        p.any_er[g * W + w] = 0;
+        const u64 a = p.active[g * W + w];
+        u64 nw = ld_cg(p.any_new + g * W + w);
+        if (!ARM) {                                             // lanes armed by the previous sweep ran their first iteration
+            nw |= ld_cg(p.first_new + g * W + w);
+            p.first_new[g * W + w] = 0;
+        }
+        const u64 stop = a & (~er | ~nw);                       // NumErasures == 0  ||  == NumErasuresPrec
+        s_act[w] = a;
+        u64 left = a & ~stop;
+        if (ARM) { left |= p.arm_mask[g * W + w]; p.arm_mask[g * W + w] = 0; }   // armed lanes start iterating with the next sweep
+        p.active[g * W + w] = left;
+        p.done_mask[g * W + w] |= stop;
+        p.fail_mask[g * W + w] |= stop & er;
+        p.any_new[g * W + w] = 0;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_act[w] >> b) & 1ull) p.lane_iter[g * p.lanes + l] += 1;
+    }
+    if (threadIdx.x == 0) p.ticket[g] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------------------
+template <typename K>
+static int resident_blocks_ns(K kernel, int block)
+{
+    int occ = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 2;
+    return occ * (sms > 0 ? sms : 148);
+}
+
+template <int DV, int DC>
+static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
+{
+    const int block = 256;
+    static int res_cn = 0, res_vn_arm = 0, res_vn_lean = 0;
+    if (!res_cn) {
+        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC>, block);
+        res_vn_arm = resident_blocks_ns(ns_vn_kernel<DV, true>, block);
+        res_vn_lean = resident_blocks_ns(ns_vn_kernel<DV, false>, block);
+    }
+    const int res_vn = arm ? res_vn_arm : res_vn_lean;
+    auto grid = [&](int resident, long long items_per_graph) {
+        long long need = (items_per_graph + block - 1) / block;
+        long long gx = need < resident ? need : resident;
+        return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+    };
+    dim3 gc = grid(res_cn, (long long)p.c1 << p.chunk_shift);
+    dim3 gv = grid(res_vn, (long long)p.n << p.chunk_shift);
+    const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
+    cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
+    if (sample) cudaEventRecord(ev[0], st);
+    g_prof.launches += 2;
+    ns_cn_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    if (sample) cudaEventRecord(ev[1], st);
+    if (arm) ns_vn_kernel<DV, true><<<gv, block, 0, st>>>(p);
+    else ns_vn_kernel<DV, false><<<gv, block, 0, st>>>(p);
+    if (sample) {
+        cudaEventRecord(ev[2], st);
+        g_prof.iter_idx[g_prof.n_samples++] = p.iter;
+    }
+}
+
+// one iteration of every graph's frame stream; arm: lanes re-armed by the preceding harvest take their new frames
+int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st)
+{
+    if (dv == 4 && dc == 8) launch_node_iteration<4, 8>(p, arm, st);
+    else if (dv == 3 && dc == 6) launch_node_iteration<3, 6>(p, arm, st);
+    else if (dv == 5 && dc == 10) launch_node_iteration<5, 10>(p, arm, st);
+    else if (dv == 3 && dc == 9) launch_node_iteration<3, 9>(p, arm, st);
+    else if (dv == 4 && dc == 12) launch_node_iteration<4, 12>(p, arm, st);
+    else return -1;
+    return 0;
+}
+
+}  // namespace scldpc

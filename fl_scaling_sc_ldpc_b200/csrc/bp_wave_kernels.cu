@@ -345,14 +345,16 @@ __global__ void __launch_bounds__(256, TRAJ ? 3 : 4) bp_vn_wave_kernel(BpParams 
 //   VN sweep: for lanes in arm_mask the outgoing messages, x and y are (re)initialised from the new frame's channel
 //             bits (drawn in place, channel_draw) instead of being computed; such lanes start iterating next sweep.
 //   retire  : per-lane iteration counters; stopped lanes go to done_mask and stay untouched (their x is a fixed point).
-//   harvest : every few iterations the finalisation kernels run on done_mask only, results are stored under the
+//   harvest : every few iterations the finalisation kernels run on fail_mask (done with erasures left) only, results are stored under the
 //             frame id, and the freed lanes get the next frame ids in ascending lane order (deterministic).
 // Only unlimited-iteration decoding streams (a capped frame would keep changing while it waits for the harvest).
 // ARM = false is the lean variant for iterations in which no lane takes a new frame (15 of 16).
 template <int DV, bool ARM>
 __global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams p)
 {
-    const int g = blockIdx.y;
+    // The CN sweep walks graphs and positions upwards; this sweep walks them downwards (vn_reverse), so each sweep starts on
+    // the rows the other one touched last -- its first gathers (and the x / y rows) are L2 hits instead of HBM reads.
+    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams
         const bool work = lane_work && idx < items;
         u128 changed = zero128(), xn = zero128(), yn = zero128(), xo = zero128(), yo = zero128();
         u128 out[DV];
-        const int v = idx >> p.chunk_shift;
+        const int v = p.vn_reverse ? p.n - 1 - (idx >> p.chunk_shift) : (idx >> p.chunk_shift);
         if (work) {
             int s[DV];
             load_row<DV>(vn_slot + (size_t)v * DV, s);
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams
         if (ARM) { left |= p.arm_mask[g * W + w]; p.arm_mask[g * W + w] = 0; }   // armed lanes start iterating with the next sweep
         p.active[g * W + w] = left;
         p.done_mask[g * W + w] |= stop;
+        p.fail_mask[g * W + w] |= stop & er;
         p.any_new[g * W + w] = 0;
     }
     __syncthreads();
@@ -526,6 +529,7 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
                 else p.lane_frame[g * p.lanes + l] = -1;
             }
             p.done_mask[g * W + w] = 0;
+            p.fail_mask[g * W + w] = 0;
             p.arm_mask[g * W + w] = armw;
             any |= armw | p.active[g * W + w];
         }
@@ -546,6 +550,7 @@ __global__ void bp_stream_init_kernel(BpParams p, int n_lanes_used)
         // every usable lane starts "done" with no frame: the first harvest only arms them
         p.done_mask[g * p.W + w] = (n_lanes_used >= lo + 64) ? ~0ull : (n_lanes_used <= lo ? 0ull : ((1ull << (n_lanes_used - lo)) - 1ull));
         p.arm_mask[g * p.W + w] = 0;
+        p.fail_mask[g * p.W + w] = 0;
         p.active[g * p.W + w] = 0;
     }
     if (threadIdx.x == 0) p.next_frame[g] = 0;

@@ -21,6 +21,7 @@ int bp_launch_window_persistent(int dv, int dc, const BpParams &p, int num_it, c
 int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
 int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
+int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
 int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
@@ -148,12 +149,17 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.swept = c.take<long long>(G * 2);
     q.arm_mask = c.take<u64>(G * W);
     q.done_mask = c.take<u64>(G * W);
+    q.fail_mask = c.take<u64>(G * W);
     q.lane_frame = c.take<int>(G * lanes);
     q.lane_iter = c.take<int>(G * lanes);
     q.next_frame = c.take<int>(G);
     q.thr = c.take<u64>(G);
     q.known = c.take<int32_t>(d->L);
-    if (flags & SCLDPC_F_STREAM) q.x = c.take<u128>(G * n * ch);      // stream mode owns its decision plane
+    if (flags & SCLDPC_F_STREAM) {
+        q.x = c.take<u128>(G * n * ch);                               // stream mode owns its decision plane
+        q.two = c.take<u128>(G * nk * ch);
+        q.first_new = c.take<u64>(G * W);
+    }
     q.cn_dis = c.take<u128>(G * nk * ch);                             // sized for the largest possible ignored head
     if (p) *p = q;
     return c.off;
@@ -471,7 +477,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     p.frames_per_graph = cfg->frames_per_graph; p.seed = cfg->seed; p.first_graph = cfg->first_graph_id;
     p.s_iters = out->iters_dev; p.s_residual = out->residual_dev; p.s_blocks_err = out->blocks_err_dev;
     p.s_erasures_exp = out->erasures_exp_dev; p.s_blocks_err_exp = out->blocks_err_exp_dev;
-    p.lane_mask = p.done_mask;
+    p.vn_reverse = env_int("SCLDPC_VN_REVERSE", 1, 0, 1);
+    p.lane_mask = p.fail_mask;                   // frames that stopped without erasures have all-zero counts already
     // per-graph channel thresholds and the doping profile
     std::vector<u64> thr(d->n_graphs);
     for (int g = 0; g < d->n_graphs; g++) {
@@ -488,10 +495,18 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     CU(cudaStreamSynchronize(st));               // host vectors leave scope at return; keep it simple
     // state: Lij = 1 (tail CNs of a truncated code are never swept), everything else 0; no lane holds a frame yet
     const size_t ch = p.chunks;
-    CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
-    CU(cudaMemsetAsync(p.v2c, 0, sizeof(u128) * (size_t)p.G * (p.E + 1) * ch, st));
+    // SCLDPC_STREAM_NODE=0 selects the message-passing sweeps (the implementation of record); the default is the node-state
+    // formulation of bp_node_kernels.cu, which yields the same erased set at every iteration with ~6x less HBM traffic
+    const bool node = env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
     CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
-    CU(cudaMemsetAsync(p.y, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+    if (node) {
+        CU(cudaMemsetAsync(p.two, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * ch, st));
+        CU(cudaMemsetAsync(p.first_new, 0, sizeof(u64) * (size_t)p.G * p.W, st));
+    } else {
+        CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
+        CU(cudaMemsetAsync(p.v2c, 0, sizeof(u128) * (size_t)p.G * (p.E + 1) * ch, st));
+        CU(cudaMemsetAsync(p.y, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+    }
     {
         BpParams q = p;                          // control words, counters, position lists ("every position")
         bp_launch_init_ctrl_only(q, d->n_frames, st);
@@ -514,7 +529,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     for (;;) {
         for (int q = 0; q < H; q++, it++) {
             p.iter = (int)(it & 0x3fffffff);
-            if (bp_launch_stream_iteration(d->dv, d->dc, p, q == 0, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+            if (node ? bp_launch_node_iteration(d->dv, d->dc, p, q == 0, st) : bp_launch_stream_iteration(d->dv, d->dc, p, q == 0, st))
+                return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);

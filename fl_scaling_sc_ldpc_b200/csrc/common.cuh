@@ -218,6 +218,9 @@ struct BpParams {
     // frame streams (lane recycling): a finished frame frees its bit lane for the next channel realisation
     u64 *arm_mask;            // [G][W] lanes that take a new frame in the next VN sweep
     u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested
+    u128 *two;                // [G][nk][chunks] node-state streams: "this CN has >= 2 erased neighbours" (bp_node_kernels.cu)
+    u64 *first_new;           // [G][W] node-state streams: lanes whose new frame has a VN the channel left known
+    u64 *fail_mask;           // [G][W] subset of done_mask that stopped with erased VNs left (the only lanes the count kernels read)
     int *lane_frame;          // [G][lanes] frame id decoded in the lane, -1 if idle
     int *lane_iter;           // [G][lanes] iterations executed by the lane's current frame
     int *next_frame;          // [G] next frame id of the graph's stream
@@ -233,6 +236,7 @@ struct BpParams {
     // per-launch
     int c0, c1, v0, v1;       // CN / VN ranges swept
     int iter;                 // iteration index inside the current loop
+    int vn_reverse;           // stream mode: the VN sweep walks graphs and VNs downwards (see bp_vn_stream_kernel)
     int max_it;               // cap of the current loop
     int first_iter;           // 1: the previous a-posteriori state is "all erased" (NumErasuresPrec = n)
     int stall_at_first;       // 1: the stall test is meaningful at first_iter (the sweep covers all n VNs)

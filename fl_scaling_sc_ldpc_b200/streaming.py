@@ -78,10 +78,17 @@ def simulate_stream(eps, dv, dc, M, W, doped_positions=(), segment=2000, max_blo
     ens = engine.Ensemble(dv, dc, segment + W + dv, M)        # positions beyond `segment` only feed the last windows
     tot = dict(num_erasures=0, num_bits_generated=0, num_blocks_err=0, num_blocks_generated=0, num_erasures_exp=0,
                num_bits_generated_exp=0, num_blocks_err_exp=0, num_blocks_generated_exp=0)
+    from . import dist as D
+    rank, world = D.world()
     gid = 0
     while True:
-        plain, ex = decode_segment(ens, W, eps, doped_positions, graphs_per_batch, frames_per_graph, seed, gid)
-        gid += graphs_per_batch
+        # one round = one batch of segments per rank (graph ids are global); the per-position counts are all-gathered and every
+        # rank replays the stop rule over the segments in order, so the row does not depend on the number of GPUs
+        plain, ex = decode_segment(ens, W, eps, doped_positions, graphs_per_batch, frames_per_graph, seed, gid + rank * graphs_per_batch)
+        gid += world * graphs_per_batch
+        if world > 1:
+            plain = D.allgather_rows(np.asarray(plain)).reshape((-1,) + plain.shape[1:])
+            ex = D.allgather_rows(np.asarray(ex)).reshape((-1,) + ex.shape[1:])
         for g in range(plain.shape[0]):
             for f in range(plain.shape[2]):
                 c = stream_counters(plain[g, :, f], ex[g, :, f], segment, dv, doped_positions, M)
@@ -131,10 +138,14 @@ def main_streaming(argv=None) -> int:
     ap.add_argument("--outdir", default=".")
     a = ap.parse_args(argv)
     doped = list(a.doped)[: a.num_doped]
+    from . import dist as D
+    rank, _world = D.init_from_env()
     name = "SC_LDPC_%d_%d_L%d_M%d_DOP%d_BP_Stream_SW%d_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.num_doped, a.W, a.index)
     for sim in range(a.points):
         eps = a.eps_ini - sim * a.eps_delta
         t = simulate_stream(eps, a.dv, a.dc, a.M * a.dc // a.dv, a.W, doped, a.segment, a.max_blocks_err, a.max_blocks, a.seed + 17 * sim)
+        if rank != 0:
+            continue
         sys.stdout.write("%f %e %e %e %e\n" % (eps, t["num_erasures"] / t["num_bits_generated"], t["num_blocks_err"] / t["num_blocks_generated"],
                                                t["num_erasures_exp"] / t["num_bits_generated_exp"], t["num_blocks_err_exp"] / t["num_blocks_generated_exp"]))
         with open(os.path.join(a.outdir, name), "w" if sim == 0 else "a") as f:

@@ -20,6 +20,9 @@ common = ["--L", "12", "--M", "32", "--outdir", out, "--seed", "5", "--points", 
 bp_cli.run("bp_lim_iter", ["1", "0", "0", "40"] + common + ["--min-frame-err", "25", "--max-frames", "600"])
 bp_cli.run("sw_lim_iter", ["2", "4", "0", "6", "12"] + common + ["--min-frame-err", "25", "--max-frames", "600"])
 bp_cli.run("bp_traj", ["3", "0", "0", "30", "1"] + common + ["--min-frame-err", "1000000", "--max-frames", "100"])
+from fl_scaling_sc_ldpc_b200 import streaming
+streaming.main_streaming(["4", "5", "0", "--L", "16", "--M", "16", "--eps-ini", "0.46", "--eps-delta", "0.02", "--points", "2", "--segment", "60",
+                          "--max-blocks-err", "30", "--max-blocks", "20000", "--outdir", out])
 # 3. peeling trajectories + the variance driver
 _, r1, plrs = pdx.simulate_peeling_decoder_ldpc(0.45, 4, 8, 12, 64, False, False, 37, seed=11)
 if rank == 0:

@@ -9,6 +9,13 @@ pytestmark = pytest.mark.gpu
 KEYS = ("iters", "residual", "blocks_err", "erasures_exp", "blocks_err_exp")
 
 
+@pytest.fixture(autouse=True, params=["node_state", "messages"])
+def stream_kernels(request, monkeypatch):
+    """both stream implementations: the node-state sweeps (bp_node_kernels.cu, default) and the message-passing sweeps"""
+    monkeypatch.setenv("SCLDPC_STREAM_NODE", "1" if request.param == "node_state" else "0")
+    return request.param
+
+
 def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
     """frames 0..B-1 decoded 128 at a time with the synchronous decoder on the same graphs"""
     G = fb_graphs.n_graphs
@@ -24,7 +31,8 @@ def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
     return out
 
 
-@pytest.mark.parametrize("L,M,lanes,B,eps", [(10, 50, 128, 700, [0.44, 0.50]), (16, 64, 100, 333, [0.47, 0.41]), (8, 32, 256, 256, [0.5, 0.3])])
+@pytest.mark.parametrize("L,M,lanes,B,eps", [(10, 50, 128, 700, [0.44, 0.50]), (16, 64, 100, 333, [0.47, 0.41]), (8, 32, 256, 256, [0.5, 0.3]),
+                                               (6, 16, 64, 150, [1.0, 0.0]), (12, 40, 512, 1500, [0.46, 0.52])])
 def test_stream_equals_synchronous_batches(L, M, lanes, B, eps):
     ens = eng.Ensemble(4, 8, L, M)
     fbg = eng.FrameBatch(ens, 2, lanes).generate_graphs(21, first_graph_id=3)
