@@ -3,130 +3,220 @@
 // From the all-erased start the messages of flooding BP on the BEC are monotone, and the a-posteriori erased set after
 // iteration t is a function of the erased set after iteration t-1 alone ("parallel peeling"):
 //
-//     x_v(t) = x_v(t-1)  AND  for every CN c of v:  c has at least two erased neighbours in x(t-1)
+//     x_v(t) = x_v(t-1)  AND NOT  (some CN of v has v as its only erased neighbour in x(t-1))
 //
-// (a CN with exactly one erased neighbour resolves it; an extrinsic message that the message-passing decoder would still
-// hold back can only concern a VN that is already known).  The erased set -- hence the residual
-// erasures, the per-frame iteration count under the reference's stall rule (NumErasures == NumErasuresPrec,
-// BP_FULL.c:1046-1066), the error counts and the expurgation inputs -- is bit-identical to decodeBP's at every iteration;
-// tests/test_node_state_gpu.py holds it against the message kernels and the compiled reference.  What the formulation does
-// not carry are the messages themselves, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) and the window decoders
-// stay on the message kernels (bp_kernels.cu / bp_wave_kernels.cu), which remain the implementation of record.
+// (an extrinsic message that the message-passing decoder would still hold back can only concern a VN that is already
+// known).  The erased set -- hence the residual erasures, the per-frame iteration count under the
+// reference's stall rule (NumErasures == NumErasuresPrec, BP_FULL.c:1046-1066), the error counts and the expurgation
+// inputs -- is bit-identical to decodeBP's at every iteration; tests/test_stream_gpu.py holds it against the message
+// kernels (themselves checked against the oracle and the compiled reference).  What the formulation does not carry are
+// the messages, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) and the window decoders stay on the message
+// kernels (bp_kernels.cu / bp_wave_kernels.cu), which remain the implementation of record.
 //
-// State per graph: x [n][chunks] (1 bit per VN and frame) and two [nk][chunks] ("this CN has >= 2 erased neighbours").
-//   CN sweep: gathers the dc x rows of a CN, writes its `two` row             (reads  E rows through L2, writes nk rows)
-//   VN sweep: x_v &= AND of the dv `two` rows of v; arms freed lanes with a new channel draw (reads E rows through L2)
-// Both gathers stay inside a band of dv positions (5 MB of x, 2.5 MB of `two` at M = 10000, 1024 frames), which lives in
-// L2; HBM only sees the sequential x / two / index streams: (2n + nk)/8 bytes per frame-iteration instead of (4E + n)/8.
+// State per graph: x and xb [n][chunks] (1 bit per VN and frame; equal between iterations).
+//   CN sweep  : gathers the dc x rows of a CN (E rows through L2: the gather stays inside a band of dv positions, 5 MB at
+//               M = 10000 and 1024 frames) and clears, in xb, the neighbour it resolves (sparse 64-bit atomics)
+//   state pass: sequential; copies the touched rows of xb to x, ORs "an erased VN is left", arms freed lanes
+// HBM sees the index stream and the sequential state pass: about n/8 bytes per frame-iteration instead of (4E + n)/8.
 //
 // Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scldpc {
 
 // ------------------------------------------------------------------------------------------------------------
-// check-node sweep: two[c] = "at least two of the neighbours of c are erased"
+// adjacency rows of the block's next trips, copied to shared memory ahead of time (cp.async): the dependent chain of a
+// trip is then one gather deep (shared-memory row -> node rows) instead of two (index row from HBM -> node rows)
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, int DC>
-__global__ void __launch_bounds__(256, 5) ns_cn_kernel(BpParams p)
+constexpr int NS_STAGES = 3;
+
+
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem)
 {
-    const int g = blockIdx.y;
-    if (ld_cg(p.alive + g) == 0) return;
-    const int ch = p.chunks;
-    const int k = threadIdx.x & (ch - 1);
-    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    if (!nz(act)) return;                                       // a thread keeps its chunk: blockDim and the stride are multiples of ch
-    const u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
-    u128 *__restrict__ two = p.two + (size_t)g * p.nk * ch;
-    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
-    const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept: two = 1
-    const int stride = gridDim.x * blockDim.x;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
-        const int c = idx >> p.chunk_shift;
-        int e[DC];
-        load_row<DC>(cn_edge + (size_t)c * DC, e);
-        u128 in[DC];
-#pragma unroll
-        for (int j = 0; j < DC; j++) in[j] = (e[j] != p.E) ? ld_stream(x + (size_t)(e[j] / DV) * ch + k) : zero128();
-        u128 one = zero128(), tw = zero128();
-#pragma unroll
-        for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
-        two[(size_t)c * ch + k] = tw;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copies `count` int32 from src to dst (both 4-byte aligned; 16-byte copies when the source allows), all threads of the block
+__device__ __forceinline__ void prefetch_ints(int *dst, const int32_t *src, int count)
+{
+    if (count <= 0) return;
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)__cvta_generic_to_shared(dst)) & 15) == 0) {
+        const int n16 = count >> 2;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async_16(dst + 4 * i, src + 4 * i);
+        for (int i = 4 * n16 + threadIdx.x; i < count; i += blockDim.x) cp_async_4(dst + i, src + i);
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) cp_async_4(dst + i, src + i);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// variable-node sweep + end of the iteration (last block): same control flow as bp_vn_stream_kernel
+// check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
+// the bit is cleared in xb, the copy that becomes the state after this iteration, so every CN of the sweep still reads the
+// old state (flooding).  Resolutions are sparse (a VN is resolved once per frame), so the scatter costs little.
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, bool ARM>
-__global__ void __launch_bounds__(256, 4) ns_vn_kernel(BpParams p)
+template <int DV, int DC, int BLK>
+__global__ void __launch_bounds__(256, BLK) ns_cn_kernel(BpParams p)
 {
-    // the CN sweep walks graphs and nodes upwards, this one downwards: each sweep starts on what the other touched last
-    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
-    __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
+    extern __shared__ __align__(16) int s_rows[];               // [NS_STAGES][256 >> chunk_shift][DC]
+    __shared__ u64 s_new[SCLDPC_MAX_WORDS];
+    if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const bool lane_work = nz(act);                             // a thread keeps its chunk: blockDim and the stride are multiples of ch
+    const u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u64 *__restrict__ xb = reinterpret_cast<u64 *>(p.xb + (size_t)g * p.n * ch);
+    unsigned char *__restrict__ dirty = p.dirty + (size_t)g * p.n * ch;
+    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const int n_cn = p.c1;                                      // CNs >= c1 (tail of a truncated code) are never swept
+    const int rows = 256 >> p.chunk_shift;                      // CNs per trip
+    const int trips_total = (n_cn + rows - 1) / rows;
+    u128 acc_new = zero128();
+    auto issue = [&](int t) {
+        const int trip = blockIdx.x + t * gridDim.x;
+        if (trip < trips_total) {
+            const int c0 = trip * rows, cnt = min(rows, n_cn - c0);
+            prefetch_ints(s_rows + (t % NS_STAGES) * rows * DC, cn_edge + (size_t)c0 * DC, cnt * DC);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int t = 0; t < NS_STAGES - 1; t++) issue(t);
+    for (int t = 0; blockIdx.x + t * gridDim.x < trips_total; t++) {
+        cp_async_wait<NS_STAGES - 2>();
+        __syncthreads();
+        issue(t + NS_STAGES - 1);
+        const int r = threadIdx.x >> p.chunk_shift;
+        const int c = (blockIdx.x + t * gridDim.x) * rows + r;
+        if (!lane_work || c >= n_cn) continue;
+        const int *row = s_rows + ((t % NS_STAGES) * rows + r) * DC;
+        u128 in[DC];
+#pragma unroll
+        for (int j = 0; j < DC; j++) {
+            const int e = row[j];
+            in[j] = (e != p.E) ? ld_stream(x + (size_t)(e / DV) * ch + k) : zero128();
+        }
+        u128 one = zero128(), tw = zero128();
+#pragma unroll
+        for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
+        const u128 res = one & ~tw;                             // frames in which exactly one neighbour of c is erased
+        if (nz(res)) {
+            acc_new |= res;
+#pragma unroll
+            for (int j = 0; j < DC; j++) {
+                const u128 clr = in[j] & res;
+                if (nz(clr)) {
+                    const size_t o = (size_t)(row[j] / DV) * ch + k;
+                    if (clr.x) atomicAnd(reinterpret_cast<unsigned long long *>(xb + 2 * o), ~clr.x);
+                    if (clr.y) atomicAnd(reinterpret_cast<unsigned long long *>(xb + 2 * o + 1), ~clr.y);
+                    dirty[o] = 1;
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    acc_new = warp_or_same_chunk(acc_new, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
+        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// state pass + end of the iteration (last block): brings x up to xb on the rows the CN sweep touched, collects "an erased
+// VN is left", arms freed lanes with their new frames' channel draws; same control flow as bp_vn_stream_kernel
+// ------------------------------------------------------------------------------------------------------------
+template <bool ARM>
+__global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ u64 s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
-    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_new[threadIdx.x] = 0; s_er[threadIdx.x] = 0; s_first[threadIdx.x] = 0; }
+    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_er[threadIdx.x] = 0; s_first[threadIdx.x] = 0; }
     __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
     const u128 arm = ARM ? reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k] : zero128();
-    const bool lane_work = nz(act | arm);
-    u128 acc_new = zero128(), acc_er = zero128(), acc_first = zero128();
-    const u128 *__restrict__ two = p.two + (size_t)g * p.nk * ch;
+    u128 acc_er = zero128(), acc_first = zero128();
     u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
-    const int32_t *__restrict__ vn_cn = p.vn_cn + (size_t)g * p.n * DV;
+    u128 *__restrict__ xb = p.xb + (size_t)g * p.n * ch;
+    unsigned char *__restrict__ dirty = p.dirty + (size_t)g * p.n * ch;
     const int items = p.n << p.chunk_shift;
     const int stride = gridDim.x * blockDim.x;
     const u64 thr = (ARM && nz(arm)) ? p.thr[g] : 0ull;
     const uint64_t gid = p.first_graph + (uint64_t)g;
-    if (lane_work)
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
-            const int v = p.vn_reverse ? p.n - 1 - (idx >> p.chunk_shift) : (idx >> p.chunk_shift);
-            int c[DV];
-            load_row<DV>(vn_cn + (size_t)v * DV, c);
-            u128 t = ld_stream(two + (size_t)c[0] * ch + k);
+    constexpr int U = 4;                                        // rows in flight per thread: the pass is a plain stream, latency-bound otherwise
+    if (nz(act | arm))
+        for (int base = blockIdx.x * blockDim.x * U + threadIdx.x; base < items; base += stride * U) {
+            u128 xs[U];
+            unsigned char ds[U];
 #pragma unroll
-            for (int i = 1; i < DV; i++) t &= ld_stream(two + (size_t)c[i] * ch + k);
-            const u128 xo = x[(size_t)v * ch + k];
-            // a stopped frame sits at a fixed point of the rule, so lanes outside `act` need no mask
-            u128 xn = xo & t;
-            if (ARM && nz(arm)) {
-                // new frames: the erased set starts as the channel's (Lji = channel value on every edge, BP_FULL.c:913-917)
-                const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
-                u128 cw = zero128();
-                // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
-                // usually shared by up to four armed lanes
-                uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
-                for (int half = 0; half < 2; half++) {
-                    u64 m = half ? arm.y : arm.x, w = 0;
-                    while (m && !forced) {
-                        const int b = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
-                        if ((fr >> 2) != blk) {
-                            blk = fr >> 2;
-                            philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
-                                          (uint32_t)(p.seed >> 32), r4);
+            for (int u = 0; u < U; u++) {
+                const int idx = base + u * (int)blockDim.x;
+                xs[u] = zero128(); ds[u] = 0;
+                if (idx < items) { xs[u] = ld_cg128(xb + idx); ds[u] = dirty[idx]; }   // the CN sweep wrote xb with atomics (L2)
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int idx = base + u * (int)blockDim.x;
+                if (idx >= items) break;
+                u128 xn = xs[u];
+                const bool d = ds[u] != 0;
+                bool wr_x = d, wr_b = false;
+                if (ARM && nz(arm)) {
+                    // new frames: the erased set starts as the channel's (Lji = channel value on every edge, BP_FULL.c:913-917)
+                    const int v = idx >> p.chunk_shift;
+                    const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
+                    u128 cw = zero128();
+                    // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
+                    // usually shared by up to four armed lanes
+                    uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
+                    for (int half = 0; half < 2; half++) {
+                        u64 m = half ? arm.y : arm.x, w = 0;
+                        while (m && !forced) {
+                            const int b = __ffsll((long long)m) - 1;
+                            m &= m - 1;
+                            const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
+                            if ((fr >> 2) != blk) {
+                                blk = fr >> 2;
+                                philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
+                                              (uint32_t)(p.seed >> 32), r4);
+                            }
+                            if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
                         }
-                        if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
+                        if (half) cw.y = w; else cw.x = w;
                     }
-                    if (half) cw.y = w; else cw.x = w;
-                }
-                xn = sel(arm, cw, xn);
-                acc_first |= ~cw & arm;                         // NumErasuresPrec = n before the first iteration: it makes
-            }                                                   // "progress" iff the channel left some VN known
-            if (neq(xn, xo)) x[(size_t)v * ch + k] = xn;
-            acc_new |= xo & ~xn & act;
-            acc_er |= xn & act;
+                    const u128 xa = sel(arm, cw, xn);
+                    if (neq(xa, xn)) { xn = xa; wr_x = true; wr_b = true; }
+                    acc_first |= ~cw & arm;                     // NumErasuresPrec = n before the first iteration: it makes
+                }                                               // "progress" iff the channel left some VN known
+                if (wr_x) x[idx] = xn;
+                if (wr_b) xb[idx] = xn;
+                if (d) dirty[idx] = 0;
+                acc_er |= xn & act;
+            }
         }
-    acc_new = warp_or_same_chunk(acc_new, ch);
     acc_er = warp_or_same_chunk(acc_er, ch);
     if (ARM) acc_first = warp_or_same_chunk(acc_first, ch);
     if ((threadIdx.x & 31) < ch) {
-        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
-        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
         if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
         if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
         if (ARM) {
@@ -137,7 +227,6 @@ __global__ void __launch_bounds__(256, 4) ns_vn_kernel(BpParams p)
     __syncthreads();
     if (threadIdx.x < p.W) {
         const int w = threadIdx.x;
-        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
         if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
         if (ARM && (s_first[w] & ~ld_cg(p.first_new + g * p.W + w))) atomicOr(p.first_new + g * p.W + w, s_first[w]);
     }
@@ -155,7 +244,7 @@ __global__ void __launch_bounds__(256, 4) ns_vn_kernel(BpParams p)
         p.any_er[g * W + w] = 0;
         const u64 a = p.active[g * W + w];
         u64 nw = ld_cg(p.any_new + g * W + w);
-        if (!ARM) {                                             // lanes armed by the previous sweep ran their first iteration
+        if (!ARM) {                                             // lanes armed by the previous pass ran their first iteration
             nw |= ld_cg(p.first_new + g * W + w);
             p.first_new[g * W + w] = 0;
         }
@@ -193,11 +282,13 @@ template <int DV, int DC>
 static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
 {
     const int block = 256;
-    static int res_cn = 0, res_vn_arm = 0, res_vn_lean = 0;
+    static int res_cn = 0, res_vn_arm = 0, res_vn_lean = 0, cn_blk = 4;
     if (!res_cn) {
-        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC>, block);
-        res_vn_arm = resident_blocks_ns(ns_vn_kernel<DV, true>, block);
-        res_vn_lean = resident_blocks_ns(ns_vn_kernel<DV, false>, block);
+        const char *e = getenv("SCLDPC_NS_CN_BLOCKS");
+        cn_blk = (e && atoi(e) == 5) ? 5 : 4;
+        res_cn = cn_blk == 5 ? resident_blocks_ns(ns_cn_kernel<DV, DC, 5>, block) : resident_blocks_ns(ns_cn_kernel<DV, DC, 4>, block);
+        res_vn_arm = resident_blocks_ns(ns_x_kernel<true>, block);
+        res_vn_lean = resident_blocks_ns(ns_x_kernel<false>, block);
     }
     const int res_vn = arm ? res_vn_arm : res_vn_lean;
     auto grid = [&](int resident, long long items_per_graph) {
@@ -206,15 +297,17 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
         return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
     };
     dim3 gc = grid(res_cn, (long long)p.c1 << p.chunk_shift);
-    dim3 gv = grid(res_vn, (long long)p.n << p.chunk_shift);
+    dim3 gv = grid(res_vn, (((long long)p.n << p.chunk_shift) + 3) / 4);          // the state pass takes four rows per thread and trip
     const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    ns_cn_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    const size_t sm_cn = sizeof(int) * NS_STAGES * (256 >> p.chunk_shift) * DC;
+    if (cn_blk == 5) ns_cn_kernel<DV, DC, 5><<<gc, block, sm_cn, st>>>(p);
+    else ns_cn_kernel<DV, DC, 4><<<gc, block, sm_cn, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
-    if (arm) ns_vn_kernel<DV, true><<<gv, block, 0, st>>>(p);
-    else ns_vn_kernel<DV, false><<<gv, block, 0, st>>>(p);
+    if (arm) ns_x_kernel<true><<<gv, block, 0, st>>>(p);
+    else ns_x_kernel<false><<<gv, block, 0, st>>>(p);
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;

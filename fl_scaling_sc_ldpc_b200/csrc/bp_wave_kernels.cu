@@ -493,48 +493,74 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
 {
     const int g = blockIdx.x, L = p.L, W = p.W, B = p.frames_per_graph;
     if (ld_cg(p.alive + g) == 0) return;
+    __shared__ int s_rank[SCLDPC_MAX_WORDS + 1];
+    __shared__ u64 s_done[SCLDPC_MAX_WORDS], s_arm[SCLDPC_MAX_WORDS];
+    __shared__ int s_frames;
+    __shared__ unsigned long long s_its;
+    if (threadIdx.x == 0) {
+        s_frames = 0; s_its = 0;
+        int r = 0;
+        for (int w = 0; w < W; w++) {
+            s_done[w] = p.done_mask[g * W + w];
+            s_arm[w] = 0;
+            s_rank[w] = r;
+            r += __popcll(s_done[w]);
+        }
+        s_rank[W] = r;
+    }
+    __syncthreads();
+    const int next0 = p.next_frame[g];
     for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
-        if (!((p.done_mask[g * W + (l >> 6)] >> (l & 63)) & 1ull)) continue;
+        const int w = l >> 6, b = l & 63;
+        if (!((s_done[w] >> b) & 1ull)) continue;
         const int fr = p.lane_frame[g * p.lanes + l];
         int residual = 0, blocks = 0, e_exp = 0, b_exp = 0, first_done = 0;
-        for (int q = 0; q < L; q++) {
-            const size_t o = ((size_t)g * L + q) * p.lanes + l;
-            const int plain = p.pos_cnt[o], ex = plain - 2 * p.pos_pairs[o];
-            p.pos_cnt[o] = 0;
-            p.pos_pairs[o] = 0;
-            residual += plain;
-            if (plain > 0) blocks++;
-            if (ex > 0 && (exp_all || !first_done)) { first_done = 1; e_exp += ex; b_exp++; }
-        }
+        // only frames that stopped with erased VNs left were counted (fail_mask): every other frame's results are zero
+        if ((p.fail_mask[g * W + w] >> b) & 1ull)
+            for (int q = 0; q < L; q++) {
+                const size_t o = ((size_t)g * L + q) * p.lanes + l;
+                const int plain = p.pos_cnt[o], ex = plain - 2 * p.pos_pairs[o];
+                if (plain) p.pos_cnt[o] = 0;
+                if (plain != ex) p.pos_pairs[o] = 0;
+                residual += plain;
+                if (plain > 0) blocks++;
+                if (ex > 0 && (exp_all || !first_done)) { first_done = 1; e_exp += ex; b_exp++; }
+            }
         if (fr >= 0 && fr < B) {
             const size_t o = (size_t)g * B + fr;
-            p.s_iters[o] = p.lane_iter[g * p.lanes + l];
+            const int its = p.lane_iter[g * p.lanes + l];
+            p.s_iters[o] = its;
+            atomicAdd(&s_frames, 1);
+            atomicAdd(&s_its, (unsigned long long)its);
             p.s_residual[o] = residual;
             p.s_blocks_err[o] = blocks;
             p.s_erasures_exp[o] = e_exp;
             p.s_blocks_err_exp[o] = b_exp;
         }
+        // freed lanes take the next frame ids in ascending lane order
+        const int nf = next0 + s_rank[w] + __popcll(s_done[w] & ((1ull << b) - 1ull));
+        if (nf < B) {
+            p.lane_frame[g * p.lanes + l] = nf;
+            p.lane_iter[g * p.lanes + l] = 0;
+            atomicOr(reinterpret_cast<unsigned long long *>(&s_arm[w]), 1ull << b);
+        } else p.lane_frame[g * p.lanes + l] = -1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        int next = p.next_frame[g];
         u64 any = 0;
         for (int w = 0; w < W; w++) {
-            u64 d = p.done_mask[g * W + w], armw = 0;
-            while (d) {
-                const int b = __ffsll((long long)d) - 1;
-                d &= d - 1;
-                const int l = w * 64 + b;
-                if (next < B) { p.lane_frame[g * p.lanes + l] = next++; p.lane_iter[g * p.lanes + l] = 0; armw |= 1ull << b; }
-                else p.lane_frame[g * p.lanes + l] = -1;
-            }
             p.done_mask[g * W + w] = 0;
             p.fail_mask[g * W + w] = 0;
-            p.arm_mask[g * W + w] = armw;
-            any |= armw | p.active[g * W + w];
+            p.arm_mask[g * W + w] = s_arm[w];
+            any |= s_arm[w] | p.active[g * W + w];
         }
-        p.next_frame[g] = next;
+        const int nn = next0 + s_rank[W];
+        p.next_frame[g] = nn < B ? nn : B;
         if (!any) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
+        // hint for the host's harvest period: mean iterations per harvested frame of the slowest graph still decoding
+        p.h_cum[2 * g] += s_frames;
+        p.h_cum[2 * g + 1] += (long long)s_its;
+        if (any && p.h_cum[2 * g] > 0) atomicMax(p.alive_total + 1 + p.harvest_parity, (int)(p.h_cum[2 * g + 1] / p.h_cum[2 * g]));
     }
 }
 

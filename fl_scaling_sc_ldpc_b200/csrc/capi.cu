@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -134,7 +135,8 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.pos_er = c.take<u64>(G * d->L * W);
     q.ticket = c.take<unsigned>(G);
     q.alive = c.take<int>(G);
-    q.alive_total = c.take<int>(1);
+    q.alive_total = c.take<int>(4);
+    q.h_cum = c.take<long long>(G * 2);
     q.cnt_dvn = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
     q.cnt_deg1 = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
     q.pos_cnt = c.take<int>(G * d->L * lanes);
@@ -157,7 +159,8 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.known = c.take<int32_t>(d->L);
     if (flags & SCLDPC_F_STREAM) {
         q.x = c.take<u128>(G * n * ch);                               // stream mode owns its decision plane
-        q.two = c.take<u128>(G * nk * ch);
+        q.xb = c.take<u128>(G * n * ch);
+        q.dirty = c.take<unsigned char>(G * n * ch);
         q.first_new = c.take<u64>(G * W);
     }
     q.cn_dis = c.take<u128>(G * nk * ch);                             // sized for the largest possible ignored head
@@ -500,7 +503,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     const bool node = env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
     CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
     if (node) {
-        CU(cudaMemsetAsync(p.two, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * ch, st));
+        CU(cudaMemsetAsync(p.xb, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+        CU(cudaMemsetAsync(p.dirty, 0, (size_t)p.G * p.n * ch, st));
         CU(cudaMemsetAsync(p.first_new, 0, sizeof(u64) * (size_t)p.G * p.W, st));
     } else {
         CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
@@ -522,7 +526,14 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     }
-    const int H = cfg->harvest_every > 0 ? cfg->harvest_every : 16;
+    // Harvest period: a harvest costs about as much as 3.4 iterations (count / pair kernels, channel draws of the re-armed
+    // lanes) and a finished frame idles H/2 iterations on average, so the best period is about sqrt(6.8 x iterations per
+    // frame).  harvest_every <= 0: adapt it to the frames harvested so far (the slowest graph still decoding); > 0: fixed.
+    const bool adaptive = cfg->harvest_every <= 0;
+    const int hc10 = env_int("SCLDPC_HARVEST_C10", 68, 1, 1000);
+    int H = adaptive ? 16 : cfg->harvest_every;
+    CU(cudaMemsetAsync(p.alive_total + 1, 0, 2 * sizeof(int), st));
+    CU(cudaMemsetAsync(p.h_cum, 0, sizeof(long long) * 2 * (size_t)p.G, st));
     long long it = 0;
     int nchunk = 0;
     bool pending[2] = {false, false};
@@ -532,11 +543,13 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
             if (node ? bp_launch_node_iteration(d->dv, d->dc, p, q == 0, st) : bp_launch_stream_iteration(d->dv, d->dc, p, q == 0, st))
                 return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
+        const int slot = nchunk & 1;
+        p.harvest_parity = slot;
+        if (adaptive) CU(cudaMemsetAsync(p.alive_total + 1 + slot, 0, sizeof(int), st));
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
         CU(cudaGetLastError());
-        const int slot = nchunk & 1;
-        CU(cudaMemcpyAsync(hf + slot, p.alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hf + 4 * slot, p.alive_total, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
         pending[slot] = true;
         nchunk++;
@@ -544,7 +557,12 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         if (pending[prev]) {
             CU(cudaEventSynchronize(ev[prev]));
             pending[prev] = false;
-            if (hf[prev] == 0) break;
+            if (hf[4 * prev] == 0) break;
+            const int mean_it = hf[4 * prev + 1 + prev];
+            if (adaptive && mean_it > 0) {
+                H = (int)(sqrt(0.1 * hc10 * mean_it) + 0.5);
+                H = H < 8 ? 8 : (H > 64 ? 64 : H);
+            }
         }
     }
     if (iters_launched_host) *iters_launched_host = it;

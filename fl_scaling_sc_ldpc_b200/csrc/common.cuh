@@ -46,6 +46,12 @@ __device__ __forceinline__ void st_stream(u128 *p, u128 v)
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 __device__ __forceinline__ u64 ld_cg(const u64 *p) { return __ldcg(p); }
+__device__ __forceinline__ u128 ld_cg128(const u128 *p)
+{
+    u128 r;
+    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
 
 // OR-reduce a u128 over the threads of a warp that share (threadIdx.x % chunks); chunks is a power of two <= 8
@@ -197,7 +203,9 @@ struct BpParams {
     u64 *pos_er;              // [G][L][W] lanes with an erased VN in position p (trajectory mode)
     unsigned *ticket;         // [G]
     int *alive;               // [G] any active lane
-    int *alive_total;         // [1] graphs with an active lane
+    int *alive_total;         // [4] graphs with an active lane; [1], [2]: largest mean iterations per harvested frame (by harvest parity)
+    long long *h_cum;         // [G][2] frame streams: frames harvested so far and the iterations they took
+    int harvest_parity;       // frame streams: which of alive_total[1..2] this harvest reports into
     int *cnt_dvn;             // [G][slots][lanes] newly resolved VNs of this iteration (trajectory mode)
     int *cnt_deg1;            // [G][slots][lanes] degree-one CNs of this iteration (trajectory mode)
     int *pos_cnt;             // [G][L][lanes] erased VNs per position (finalisation)
@@ -218,7 +226,8 @@ struct BpParams {
     // frame streams (lane recycling): a finished frame frees its bit lane for the next channel realisation
     u64 *arm_mask;            // [G][W] lanes that take a new frame in the next VN sweep
     u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested
-    u128 *two;                // [G][nk][chunks] node-state streams: "this CN has >= 2 erased neighbours" (bp_node_kernels.cu)
+    u128 *xb;                 // [G][n][chunks] node-state streams: the erased set being built by this iteration's CN sweep (bp_node_kernels.cu)
+    unsigned char *dirty;     // [G][n*chunks] node-state streams: rows of xb the CN sweep cleared bits in
     u64 *first_new;           // [G][W] node-state streams: lanes whose new frame has a VN the channel left known
     u64 *fail_mask;           // [G][W] subset of done_mask that stopped with erased VNs left (the only lanes the count kernels read)
     int *lane_frame;          // [G][lanes] frame id decoded in the lane, -1 if idle

@@ -278,7 +278,7 @@ class StreamResult:
 
 
 def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, first_graph_id: int = 0, is_term: bool = True,
-                     doping_points=(), harvest_every: int = 16, exp_all: bool = False, collect: bool = True):
+                     doping_points=(), harvest_every: int = 0, exp_all: bool = False, collect: bool = True):
     """Unlimited-iteration full BP over a stream of ``frames_per_graph`` frames per graph with lane recycling
     (``scldpc_bp_stream``).  Frame f of graph g is the channel realisation ``generate_erasures(..., first_frame=...)``
     puts in lane f - first_frame; the graphs are the ones resident in ``fb`` (``fb.n_frames`` lanes are used)."""

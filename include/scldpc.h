@@ -139,7 +139,7 @@ int scldpc_bp_set_unscanned_head(int n_cns);
  * int32 [G][frames_per_graph].  b->chan_dev is not used. */
 typedef struct {
     int32_t frames_per_graph;        /* stream length per graph                                                */
-    int32_t harvest_every;           /* iterations between harvests (<= 0: 16)                                 */
+    int32_t harvest_every;           /* iterations between harvests (<= 0: adapted to the iterations per frame) */
     uint32_t flags;                  /* SCLDPC_F_TERMINATED, SCLDPC_F_EXP_ALL                                  */
     int32_t n_doped, n_soft;
     const double *eps_host;          /* [G] erasure probability of each graph's channel                        */

@@ -73,3 +73,27 @@ def test_stream_full_size_sample():
             out[k].append(getattr(r, k))
     for k in KEYS:
         assert (getattr(s, k) == np.concatenate(out[k], axis=1)).all(), k
+
+
+def test_stream_matches_oracle_directly():
+    """stream results against the CPU oracle (decodeBP restatement) on the very channel realisations the stream draws"""
+    import oracle
+    dv, dc, L, M, G, B = 4, 8, 14, 40, 2, 260
+    ens = eng.Ensemble(dv, dc, L, M)
+    fbg = eng.FrameBatch(ens, G, 128).generate_graphs(31, first_graph_id=3)
+    eps = [0.45, 0.50]
+    vn = fbg.vn_cn.cpu().numpy()
+    for is_term in (True, False):
+        s = eng.decode_bp_stream(fbg, B, eps, 77, first_graph_id=3, is_term=is_term)
+        for f0 in range(0, B, 128):
+            k = min(128, B - f0)
+            fb = eng.FrameBatch(ens, G, k, 2)
+            fb.vn_cn.copy_(fbg.vn_cn); fb._build_tables()
+            fb.generate_erasures(eps, 77, first_graph_id=3, first_frame=f0)
+            ch = fb.erasures_host()
+            for g in range(G):
+                gg = oracle.Graph(vn[g], L, M, ens.cns_pos, dv, dc)
+                for f in range(0, k, 3):
+                    o = oracle.decode_bp(gg, ch[g, f].astype(np.int32), 10 ** 9, int(is_term))
+                    got = (s.iters[g, f0 + f], s.residual[g, f0 + f], s.blocks_err[g, f0 + f], s.erasures_exp[g, f0 + f], s.blocks_err_exp[g, f0 + f])
+                    assert got == (o["iters"], o["residual"], o["blocks_err"], o["erasures_exp"], o["blocks_err_exp"]), (is_term, g, f0 + f)
