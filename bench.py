@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...   the reference's CPU decoder on the host cores
 
 A *step* decodes 4 graph realisations (one per eps of the 0.46..0.49 sweep of BASELINE config 2) x B frames each
-(default B = 8192, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
+(default B = 16384, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
 or finished.  Default mode "stream": a lane whose frame has stopped is re-armed with the graph's next channel
 realisation (scldpc_bp_stream); mode "batch": B = lanes, every lane decodes one frame (scldpc_bp_full).  Throughput counts USEFUL
 work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same formula as for the CPU
@@ -14,8 +14,11 @@ work only: edge-updates = sum over frames of (iterations that frame executed) * 
 value : batches resident in HBM, decode + per-frame counters on the device.
 e2e   : the same step through the host-buffer C-ABI call scldpc_decode_host: graph tables and bit-sliced channel
         words start in pinned HOST memory, results end in host memory; H2D / D2H inside the timed region.
-roofline : the VN sweep (dominant kernel), algorithmic bytes (2E+n)/8 per frame-iteration over CUDA-event time of
-        sampled launches inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth.
+roofline : one flooding iteration of the stream decoder (node-state sweeps: ns_cn_kernel + ns_x_kernel), algorithmic bytes
+        B_alg = (4E+n)/8 per useful frame-iteration (the message formulation's figure) over the CUDA-event time
+        of sampled launches inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth; the DRAM bytes ncu
+        measured and the node-state minimum are reported beside it.  SCLDPC_STREAM_NODE=0 / --mode batch run the
+        message-passing sweeps, for which the VN sweep is reported as before.
 cpu_baseline : the unmodified reference decodeBP (oracle/_ref, compiled from /root/reference) on the host cores.
 """
 from __future__ import annotations
@@ -40,7 +43,7 @@ N_VNS = L * M
 N_CNS = (L + DV - 1) * (M * DV // DC)
 WORKLOAD = ("full BP unlimited iterations, (4,8) SC-LDPC terminated L=50 M=10000, BEC eps sweep "
             "{0.46,0.47,0.48,0.49}: 4 graphs x B frames per step")
-FRAMES_PER_STREAM = 8192
+FRAMES_PER_STREAM = 16384
 HARVEST_EVERY = 0        # 0: the library adapts the period to the iterations per frame it observes
 CAP_LO = 2   # reference arm: iterations of the shorter of the two capped runs
 METRIC = "edge-updates/s (frames/s alongside), (4,8) SC-LDPC L=50 M=10000 BEC BP"

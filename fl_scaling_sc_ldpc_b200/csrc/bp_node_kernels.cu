@@ -45,16 +45,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// copies `count` int32 from src to dst (both 4-byte aligned; 16-byte copies when the source allows), all threads of the block
-__device__ __forceinline__ void prefetch_ints(int *dst, const int32_t *src, int count)
+// copies `count` int32 from src to dst (both 4-byte aligned; 16-byte copies when both allow), by the lanes of one warp
+__device__ __forceinline__ void prefetch_ints_warp(int *dst, const int32_t *src, int count, int lane)
 {
     if (count <= 0) return;
     if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)__cvta_generic_to_shared(dst)) & 15) == 0) {
         const int n16 = count >> 2;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async_16(dst + 4 * i, src + 4 * i);
-        for (int i = 4 * n16 + threadIdx.x; i < count; i += blockDim.x) cp_async_4(dst + i, src + i);
+        for (int i = lane; i < n16; i += 32) cp_async_16(dst + 4 * i, src + 4 * i);
+        for (int i = 4 * n16 + lane; i < count; i += 32) cp_async_4(dst + i, src + i);
     } else {
-        for (int i = threadIdx.x; i < count; i += blockDim.x) cp_async_4(dst + i, src + i);
+        for (int i = lane; i < count; i += 32) cp_async_4(dst + i, src + i);
     }
 }
 
@@ -68,39 +68,44 @@ __global__ void __launch_bounds__(256, BLK) ns_cn_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
-    extern __shared__ __align__(16) int s_rows[];               // [NS_STAGES][256 >> chunk_shift][DC]
+    extern __shared__ __align__(16) int s_rows[];               // [8 warps][NS_STAGES][32 >> chunk_shift][DC]
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
+    __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    const bool lane_work = nz(act);                             // a thread keeps its chunk: blockDim and the stride are multiples of ch
+    const bool lane_work = nz(act);                             // a thread keeps its chunk: 32 and the strides are multiples of ch
     const u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
     u64 *__restrict__ xb = reinterpret_cast<u64 *>(p.xb + (size_t)g * p.n * ch);
     unsigned char *__restrict__ dirty = p.dirty + (size_t)g * p.n * ch;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
     const int n_cn = p.c1;                                      // CNs >= c1 (tail of a truncated code) are never swept
-    const int rows = 256 >> p.chunk_shift;                      // CNs per trip
+    // every warp runs its own pipeline (no block barrier in the loop): trip t of warp gw covers CNs [(gw + t WG) rows, +rows)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rows = 32 >> p.chunk_shift;
     const int trips_total = (n_cn + rows - 1) / rows;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wid, WG = gridDim.x * (blockDim.x >> 5);
+    int *my_rows = s_rows + wid * NS_STAGES * rows * DC;
     u128 acc_new = zero128();
     auto issue = [&](int t) {
-        const int trip = blockIdx.x + t * gridDim.x;
+        const int trip = gw + t * WG;
         if (trip < trips_total) {
             const int c0 = trip * rows, cnt = min(rows, n_cn - c0);
-            prefetch_ints(s_rows + (t % NS_STAGES) * rows * DC, cn_edge + (size_t)c0 * DC, cnt * DC);
+            prefetch_ints_warp(my_rows + (t % NS_STAGES) * rows * DC, cn_edge + (size_t)c0 * DC, cnt * DC, lane);
         }
         cp_async_commit();
     };
 #pragma unroll
     for (int t = 0; t < NS_STAGES - 1; t++) issue(t);
-    for (int t = 0; blockIdx.x + t * gridDim.x < trips_total; t++) {
+    for (int t = 0; gw + t * WG < trips_total; t++) {
         cp_async_wait<NS_STAGES - 2>();
-        __syncthreads();
+        __syncwarp();
         issue(t + NS_STAGES - 1);
-        const int r = threadIdx.x >> p.chunk_shift;
-        const int c = (blockIdx.x + t * gridDim.x) * rows + r;
+        const int r = lane >> p.chunk_shift;
+        const int c = (gw + t * WG) * rows + r;
         if (!lane_work || c >= n_cn) continue;
-        const int *row = s_rows + ((t % NS_STAGES) * rows + r) * DC;
+        const int *row = my_rows + ((t % NS_STAGES) * rows + r) * DC;
         u128 in[DC];
 #pragma unroll
         for (int j = 0; j < DC; j++) {
@@ -302,7 +307,7 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    const size_t sm_cn = sizeof(int) * NS_STAGES * (256 >> p.chunk_shift) * DC;
+    const size_t sm_cn = sizeof(int) * NS_STAGES * (256 >> p.chunk_shift) * DC;     // 8 warps x stages x (32 >> shift) rows
     if (cn_blk == 5) ns_cn_kernel<DV, DC, 5><<<gc, block, sm_cn, st>>>(p);
     else ns_cn_kernel<DV, DC, 4><<<gc, block, sm_cn, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
