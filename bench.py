@@ -237,15 +237,18 @@ def run_ours(args):
 
     counters = torch.zeros(4, dtype=torch.int64, device=dev)   # frame-iterations, frames, frame errors, bit errors
 
+    iters_launched = [0]                                       # sweep pairs launched by this rank in the timed region
+
     def step(i, acc=True):
         fb = batches[i % 2]
         if stream_mode:
-            res, _ = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=fb.gid0, harvest_every=args.harvest_every, collect=False)
+            res, launched = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=fb.gid0, harvest_every=args.harvest_every, collect=False)
             it, resid = res[0].to(torch.int64), res[1].to(torch.int64)
         else:
             res, erased, rows, launched = eng.decode_bp_full(fb, eng.UNLIMITED, True, collect=False)
             it, resid = res[0, :, :lanes].to(torch.int64), res[1, :, :lanes].to(torch.int64)
         if acc:
+            iters_launched[0] += int(launched)
             counters.add_(torch.stack([it.sum(), torch.tensor(it.numel(), device=dev), (resid > 0).sum(), resid.sum()]))
 
     def barrier():
@@ -258,7 +261,7 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: K steps, device-resident inputs ---------------------------------------------------------
-    sample_every = 7        # co-prime with the harvest period (16), so sampled launches are representative
+    sample_every = 13       # co-prime with the harvest periods in use, so sampled launches are representative
     _lib.check(lib.scldpc_profile_begin(sample_every, 16384))
     lib.scldpc_launch_count(1)
     clocks = ClockSampler(local_rank)
@@ -304,7 +307,7 @@ def run_ours(args):
         n_s = ns.value
         cn_avg = float(np.mean(cn_ms[:n_s])) * 1e-3
         vn_avg = float(np.mean(vn_ms[:n_s])) * 1e-3
-        n_iter_launches = n_s * sample_every                      # iterations launched by this rank in the timed region
+        n_iter_launches = iters_launched[0] or n_s * sample_every  # iterations launched by this rank in the timed region
         fi_per_launch = local_frame_iters / max(1, n_iter_launches)
         cn_bytes = fi_per_launch * (2 * E_EDGES) / 8.0
         vn_bytes = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0

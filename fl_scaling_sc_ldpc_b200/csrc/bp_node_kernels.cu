@@ -27,110 +27,58 @@
 namespace scldpc {
 
 // ------------------------------------------------------------------------------------------------------------
-// adjacency rows of the block's next trips, copied to shared memory ahead of time (cp.async): the dependent chain of a
-// trip is then one gather deep (shared-memory row -> node rows) instead of two (index row from HBM -> node rows)
-// ------------------------------------------------------------------------------------------------------------
-constexpr int NS_STAGES = 3;
-
-
-__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// copies `count` int32 from src to dst (both 4-byte aligned; 16-byte copies when both allow), by the lanes of one warp
-__device__ __forceinline__ void prefetch_ints_warp(int *dst, const int32_t *src, int count, int lane)
-{
-    if (count <= 0) return;
-    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)__cvta_generic_to_shared(dst)) & 15) == 0) {
-        const int n16 = count >> 2;
-        for (int i = lane; i < n16; i += 32) cp_async_16(dst + 4 * i, src + 4 * i);
-        for (int i = 4 * n16 + lane; i < count; i += 32) cp_async_4(dst + i, src + i);
-    } else {
-        for (int i = lane; i < count; i += 32) cp_async_4(dst + i, src + i);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
 // the bit is cleared in xb, the copy that becomes the state after this iteration, so every CN of the sweep still reads the
 // old state (flooding).  Resolutions are sparse (a VN is resolved once per frame), so the scatter costs little.
+// The sweep is bound by instruction issue and L2 latency, not by HBM: it is kept as lean as possible (a cp.async pipeline
+// for the index rows was measured: no gain, +25 % instructions).
 // ------------------------------------------------------------------------------------------------------------
 template <int DV, int DC, int BLK>
 __global__ void __launch_bounds__(256, BLK) ns_cn_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
-    extern __shared__ __align__(16) int s_rows[];               // [8 warps][NS_STAGES][32 >> chunk_shift][DC]
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
     __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
-    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    const bool lane_work = nz(act);                             // a thread keeps its chunk: 32 and the strides are multiples of ch
-    const u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
-    u64 *__restrict__ xb = reinterpret_cast<u64 *>(p.xb + (size_t)g * p.n * ch);
-    unsigned char *__restrict__ dirty = p.dirty + (size_t)g * p.n * ch;
+    const bool lane_work = nz(reinterpret_cast<const u128 *>(p.active)[g * ch + k]);   // a thread keeps its chunk
+    const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
+    u64 *__restrict__ xbk = reinterpret_cast<u64 *>(p.xb + (size_t)g * p.n * ch + k);
+    unsigned char *__restrict__ dirtyk = p.dirty + (size_t)g * p.n * ch + k;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
-    const int n_cn = p.c1;                                      // CNs >= c1 (tail of a truncated code) are never swept
-    // every warp runs its own pipeline (no block barrier in the loop): trip t of warp gw covers CNs [(gw + t WG) rows, +rows)
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int rows = 32 >> p.chunk_shift;
-    const int trips_total = (n_cn + rows - 1) / rows;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + wid, WG = gridDim.x * (blockDim.x >> 5);
-    int *my_rows = s_rows + wid * NS_STAGES * rows * DC;
+    const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept
+    const int stride = gridDim.x * blockDim.x;
+    const int E = p.E;
     u128 acc_new = zero128();
-    auto issue = [&](int t) {
-        const int trip = gw + t * WG;
-        if (trip < trips_total) {
-            const int c0 = trip * rows, cnt = min(rows, n_cn - c0);
-            prefetch_ints_warp(my_rows + (t % NS_STAGES) * rows * DC, cn_edge + (size_t)c0 * DC, cnt * DC, lane);
-        }
-        cp_async_commit();
-    };
+    if (lane_work)
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+            const int32_t *row = cn_edge + (size_t)(idx >> p.chunk_shift) * DC;
+            int e[DC];
+            load_row<DC>(row, e);
+            u128 in[DC];
 #pragma unroll
-    for (int t = 0; t < NS_STAGES - 1; t++) issue(t);
-    for (int t = 0; gw + t * WG < trips_total; t++) {
-        cp_async_wait<NS_STAGES - 2>();
-        __syncwarp();
-        issue(t + NS_STAGES - 1);
-        const int r = lane >> p.chunk_shift;
-        const int c = (gw + t * WG) * rows + r;
-        if (!lane_work || c >= n_cn) continue;
-        const int *row = my_rows + ((t % NS_STAGES) * rows + r) * DC;
-        u128 in[DC];
+            for (int j = 0; j < DC; j++) in[j] = (e[j] != E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
+            u128 one = zero128(), tw = zero128();
 #pragma unroll
-        for (int j = 0; j < DC; j++) {
-            const int e = row[j];
-            in[j] = (e != p.E) ? ld_stream(x + (size_t)(e / DV) * ch + k) : zero128();
-        }
-        u128 one = zero128(), tw = zero128();
+            for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
+            const u128 res = one & ~tw;                         // frames in which exactly one neighbour of c is erased
+            if (nz(res)) {
+                acc_new |= res;
+                load_row<DC>(row, e);                           // L1 hit; cheaper than keeping the row live across the gather
 #pragma unroll
-        for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
-        const u128 res = one & ~tw;                             // frames in which exactly one neighbour of c is erased
-        if (nz(res)) {
-            acc_new |= res;
-#pragma unroll
-            for (int j = 0; j < DC; j++) {
-                const u128 clr = in[j] & res;
-                if (nz(clr)) {
-                    const size_t o = (size_t)(row[j] / DV) * ch + k;
-                    if (clr.x) atomicAnd(reinterpret_cast<unsigned long long *>(xb + 2 * o), ~clr.x);
-                    if (clr.y) atomicAnd(reinterpret_cast<unsigned long long *>(xb + 2 * o + 1), ~clr.y);
-                    dirty[o] = 1;
+                for (int j = 0; j < DC; j++) {
+                    const u128 clr = in[j] & res;
+                    if (nz(clr)) {
+                        const unsigned o = (unsigned)((e[j] / DV) << p.chunk_shift);
+                        if (clr.x) atomicAnd(reinterpret_cast<unsigned long long *>(xbk + 2 * (size_t)o), ~clr.x);
+                        if (clr.y) atomicAnd(reinterpret_cast<unsigned long long *>(xbk + 2 * (size_t)o + 1), ~clr.y);
+                        dirtyk[o] = 1;
+                    }
                 }
             }
         }
-    }
-    cp_async_wait<0>();
     acc_new = warp_or_same_chunk(acc_new, ch);
     if ((threadIdx.x & 31) < ch) {
         if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
@@ -307,9 +255,8 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    const size_t sm_cn = sizeof(int) * NS_STAGES * (256 >> p.chunk_shift) * DC;     // 8 warps x stages x (32 >> shift) rows
-    if (cn_blk == 5) ns_cn_kernel<DV, DC, 5><<<gc, block, sm_cn, st>>>(p);
-    else ns_cn_kernel<DV, DC, 4><<<gc, block, sm_cn, st>>>(p);
+    if (cn_blk == 5) ns_cn_kernel<DV, DC, 5><<<gc, block, 0, st>>>(p);
+    else ns_cn_kernel<DV, DC, 4><<<gc, block, 0, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
     if (arm) ns_x_kernel<true><<<gv, block, 0, st>>>(p);
     else ns_x_kernel<false><<<gv, block, 0, st>>>(p);
