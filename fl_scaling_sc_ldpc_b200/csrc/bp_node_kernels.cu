@@ -20,11 +20,11 @@
 // HBM sees the index stream and the sequential state pass: about n/8 bytes per frame-iteration instead of (4E + n)/8.
 //
 // Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace scldpc {
+
+constexpr int NS_X_ROWS = 4;
 
 // ------------------------------------------------------------------------------------------------------------
 // check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
@@ -33,8 +33,8 @@ namespace scldpc {
 // The sweep is bound by instruction issue and L2 latency, not by HBM: it is kept as lean as possible (a cp.async pipeline
 // for the index rows was measured: no gain, +25 % instructions).
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, int DC, int BLK>
-__global__ void __launch_bounds__(256, BLK) ns_cn_kernel(BpParams p)
+template <int DV, int DC>
+__global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
     const int stride = gridDim.x * blockDim.x;
     const u64 thr = (ARM && nz(arm)) ? p.thr[g] : 0ull;
     const uint64_t gid = p.first_graph + (uint64_t)g;
-    constexpr int U = 4;                                        // rows in flight per thread: the pass is a plain stream, latency-bound otherwise
+    constexpr int U = NS_X_ROWS;                                // rows in flight per thread: the pass is a plain stream
     if (nz(act | arm))
         for (int base = blockIdx.x * blockDim.x * U + threadIdx.x; base < items; base += stride * U) {
             u128 xs[U];
@@ -235,31 +235,27 @@ template <int DV, int DC>
 static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
 {
     const int block = 256;
-    static int res_cn = 0, res_vn_arm = 0, res_vn_lean = 0, cn_blk = 4;
+    static int res_cn = 0, res_x = 0;
     if (!res_cn) {
-        const char *e = getenv("SCLDPC_NS_CN_BLOCKS");
-        cn_blk = (e && atoi(e) == 5) ? 5 : 4;
-        res_cn = cn_blk == 5 ? resident_blocks_ns(ns_cn_kernel<DV, DC, 5>, block) : resident_blocks_ns(ns_cn_kernel<DV, DC, 4>, block);
-        res_vn_arm = resident_blocks_ns(ns_x_kernel<true>, block);
-        res_vn_lean = resident_blocks_ns(ns_x_kernel<false>, block);
+        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC>, block);
+        res_x = resident_blocks_ns(ns_x_kernel<true>, block);
     }
-    const int res_vn = arm ? res_vn_arm : res_vn_lean;
+    // every graph gets enough blocks to fill the machine on its own: blocks of finished graphs return at once
     auto grid = [&](int resident, long long items_per_graph) {
         long long need = (items_per_graph + block - 1) / block;
         long long gx = need < resident ? need : resident;
         return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
     };
     dim3 gc = grid(res_cn, (long long)p.c1 << p.chunk_shift);
-    dim3 gv = grid(res_vn, (((long long)p.n << p.chunk_shift) + 3) / 4);          // the state pass takes four rows per thread and trip
+    dim3 gx = grid(res_x, (((long long)p.n << p.chunk_shift) + NS_X_ROWS - 1) / NS_X_ROWS);
     const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    if (cn_blk == 5) ns_cn_kernel<DV, DC, 5><<<gc, block, 0, st>>>(p);
-    else ns_cn_kernel<DV, DC, 4><<<gc, block, 0, st>>>(p);
+    ns_cn_kernel<DV, DC><<<gc, block, 0, st>>>(p);
     if (sample) cudaEventRecord(ev[1], st);
-    if (arm) ns_x_kernel<true><<<gv, block, 0, st>>>(p);
-    else ns_x_kernel<false><<<gv, block, 0, st>>>(p);
+    if (arm) ns_x_kernel<true><<<gx, block, 0, st>>>(p);
+    else ns_x_kernel<false><<<gx, block, 0, st>>>(p);
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
