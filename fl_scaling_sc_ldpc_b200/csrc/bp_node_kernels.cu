@@ -30,12 +30,15 @@ constexpr int NS_X_ROWS = 4;
 // check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
 // the bit is cleared in xb, the copy that becomes the state after this iteration, so every CN of the sweep still reads the
 // old state (flooding).  Resolutions are sparse (a VN is resolved once per frame), so the scatter costs little.
-// The sweep is bound by instruction issue and L2 latency, not by HBM: it is kept as lean as possible (a cp.async pipeline
-// for the index rows was measured: no gain, +25 % instructions).
+// The sweep is bound by L2 latency and instruction issue, not by HBM.  Measured and dropped: a cp.async pipeline for the
+// index rows (no gain, +25 % instructions), a register prefetch of the next index row (-8 %), five blocks per SM at 48
+// registers (-2 %).  The index of the neighbour to clear is carried in bit planes next to the saturating count, which
+// keeps the divergent scatter at ~30 instructions per resolution.
 // ------------------------------------------------------------------------------------------------------------
 template <int DV, int DC>
 __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 {
+    static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
     const int k = threadIdx.x & (ch - 1);
     const bool lane_work = nz(reinterpret_cast<const u128 *>(p.active)[g * ch + k]);   // a thread keeps its chunk
     const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
-    u64 *__restrict__ xbk = reinterpret_cast<u64 *>(p.xb + (size_t)g * p.n * ch + k);
+    unsigned *__restrict__ xbk = reinterpret_cast<unsigned *>(p.xb + (size_t)g * p.n * ch + k);
     unsigned char *__restrict__ dirtyk = p.dirty + (size_t)g * p.n * ch + k;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
     const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept
@@ -60,20 +63,36 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
             u128 in[DC];
 #pragma unroll
             for (int j = 0; j < DC; j++) in[j] = (e[j] != E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
-            u128 one = zero128(), tw = zero128();
+            // saturating count of erased neighbours (one / two planes) and, in bit planes b0..b3, the index j of an erased
+            // neighbour -- exact where it is needed, i.e. in the frames with exactly one
+            u128 one = zero128(), tw = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
 #pragma unroll
-            for (int j = 0; j < DC; j++) { tw |= one & in[j]; one |= in[j]; }
+            for (int j = 0; j < DC; j++) {
+                tw |= one & in[j];
+                one |= in[j];
+                if (j & 1) b0 |= in[j];
+                if (j & 2) b1 |= in[j];
+                if (j & 4) b2 |= in[j];
+                if (j & 8) b3 |= in[j];
+            }
             const u128 res = one & ~tw;                         // frames in which exactly one neighbour of c is erased
             if (nz(res)) {
                 acc_new |= res;
-                load_row<DC>(row, e);                           // L1 hit; cheaper than keeping the row live across the gather
+                const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
+                const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
+                const unsigned w1[4] = {(unsigned)b1.x, (unsigned)(b1.x >> 32), (unsigned)b1.y, (unsigned)(b1.y >> 32)};
+                const unsigned w2[4] = {(unsigned)b2.x, (unsigned)(b2.x >> 32), (unsigned)b2.y, (unsigned)(b2.y >> 32)};
+                const unsigned w3[4] = {(unsigned)b3.x, (unsigned)(b3.x >> 32), (unsigned)b3.y, (unsigned)(b3.y >> 32)};
 #pragma unroll
-                for (int j = 0; j < DC; j++) {
-                    const u128 clr = in[j] & res;
-                    if (nz(clr)) {
-                        const unsigned o = (unsigned)((e[j] / DV) << p.chunk_shift);
-                        if (clr.x) atomicAnd(reinterpret_cast<unsigned long long *>(xbk + 2 * (size_t)o), ~clr.x);
-                        if (clr.y) atomicAnd(reinterpret_cast<unsigned long long *>(xbk + 2 * (size_t)o + 1), ~clr.y);
+                for (int q = 0; q < 4; q++) {
+                    unsigned m = rw[q];
+                    while (m) {
+                        const int b = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
+                        if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
+                        const unsigned o = (unsigned)((__ldg(row + j) / DV) << p.chunk_shift);    // L1 hit
+                        atomicAnd(xbk + 4 * (size_t)o + q, ~(1u << b));
                         dirtyk[o] = 1;
                     }
                 }
