@@ -338,9 +338,12 @@ def run_ours(args):
                                    "by L2 (a band of dv positions); HBM traffic per iteration is a fraction of B_alg, so frac > 1 is expected. "
                                    "The kernels are bound by L2->SM sector bandwidth: see l2 below",
                     "l2": {"bytes_per_launch": tn.get("cn_l2_read_bytes_per_launch"), "note": tn.get("l2_note")}}
-            kernels = {"ns_cn_kernel<4,8>": {"avg_launch_ms": 1e3 * cn_avg, "share_of_iteration": cn_avg / (cn_avg + vn_avg),
+            pct = lambda a, q: float(np.percentile(np.asarray(a[:n_s], dtype=np.float64), q))
+            kernels = {"ns_cn_kernel<4,8>": {"avg_launch_ms": 1e3 * cn_avg, "p10_p50_p90_ms": [pct(cn_ms, 10), pct(cn_ms, 50), pct(cn_ms, 90)],
+                                             "share_of_iteration": cn_avg / (cn_avg + vn_avg),
                                              "dram_bytes_per_launch": tn.get("cn_dram_bytes_per_launch")},
-                       "ns_x_kernel": {"avg_launch_ms": 1e3 * vn_avg, "share_of_iteration": vn_avg / (cn_avg + vn_avg),
+                       "ns_x_kernel": {"avg_launch_ms": 1e3 * vn_avg, "p10_p50_p90_ms": [pct(vn_ms, 10), pct(vn_ms, 50), pct(vn_ms, 90)],
+                                       "share_of_iteration": vn_avg / (cn_avg + vn_avg),
                                        "dram_bytes_per_launch": tn.get("x_dram_bytes_per_launch")}}
         else:
             traffic = tj.get("vn_sweep_dram_bytes_per_launch")

@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
         const int w = threadIdx.x;
         if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
         if (ARM && (s_first[w] & ~ld_cg(p.first_new + g * p.W + w))) atomicOr(p.first_new + g * p.W + w, s_first[w]);
+        __threadfence();                                        // only these words are read by the graph's last block
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
     __syncthreads();

@@ -58,6 +58,19 @@ def test_stream_with_doping_and_other_degrees():
         assert (getattr(s, key) == ref[key]).all(), key
 
 
+@pytest.mark.parametrize("dv,dc,L,M", [(4, 12, 9, 48), (5, 10, 8, 40), (3, 9, 10, 36)])
+def test_stream_every_instantiated_degree(dv, dc, L, M):
+    """the degree pairs the kernels are instantiated for, terminated and truncated, 192 lanes / 500 frames"""
+    ens = eng.Ensemble(dv, dc, L, M)
+    fbg = eng.FrameBatch(ens, 2, 192).generate_graphs(13, first_graph_id=3)
+    eps = [0.9 * dv / dc, 1.15 * dv / dc]
+    for is_term in (True, False):
+        ref = sync_reference(fbg, ens, 500, eps, 21, is_term)
+        s = eng.decode_bp_stream(fbg, 500, eps, 21, first_graph_id=3, is_term=is_term)
+        for key in KEYS:
+            assert (getattr(s, key) == ref[key]).all(), (is_term, key)
+
+
 def test_stream_full_size_sample():
     """(4,8), L=50, M=10000, eps=0.47: a 256-lane stream of 384 frames against synchronous decoding of the same frames"""
     ens = eng.Ensemble(4, 8, 50, 10000)
