@@ -450,6 +450,80 @@ __global__ void __launch_bounds__(256) bp_pairs_kernel(BpParams p)
     }
 }
 
+// Stream-mode variant in two passes (the prefilter above gathers dc rows for each of up to dv CNs of every erased VN, i.e.
+// several CN sweeps' worth when a stuck wave leaves half the VNs of a frame erased):
+//   bp_ex2_kernel   : per CN, "exactly two erased neighbours" among the selected lanes          (one CN sweep)
+//   bp_pairs2_kernel: per erased VN a, AND of that plane over its dv CNs, then the same per-lane check as above
+template <int DV, int DC>
+__global__ void __launch_bounds__(256) bp_ex2_kernel(BpParams p)
+{
+    const int g = blockIdx.y, ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 mask = reinterpret_cast<const u128 *>(p.lane_mask)[g * ch + k];
+    if (!nz(mask)) return;
+    const u128 *xk = p.x + (size_t)g * p.n * ch + k;
+    u128 *ex2 = p.ex2 + (size_t)g * p.nk * ch;
+    const int32_t *cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const long long items = (long long)p.nk << p.chunk_shift;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx >> p.chunk_shift);
+        int e[DC];
+        load_row<DC>(cn_edge + (size_t)c * DC, e);
+        u128 one = zero128(), two = zero128(), three = zero128();
+#pragma unroll
+        for (int j = 0; j < DC; j++) {
+            const u128 xu = (e[j] != p.E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
+            three |= two & xu; two |= one & xu; one |= xu;
+        }
+        ex2[(size_t)c * ch + k] = two & ~three & mask;
+    }
+}
+
+template <int DV, int DC>
+__global__ void __launch_bounds__(256) bp_pairs2_kernel(BpParams p)
+{
+    const int g = blockIdx.y, ch = p.chunks;
+    const u128 *x = p.x + (size_t)g * p.n * ch;
+    const u128 *ex2 = p.ex2 + (size_t)g * p.nk * ch;
+    const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * DV;
+    const int32_t *cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const long long items = (long long)p.n << p.chunk_shift;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 mask = reinterpret_cast<const u128 *>(p.lane_mask)[g * ch + k];
+    if (!nz(mask)) return;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(idx >> p.chunk_shift);
+        u128 cand = x[(size_t)a * ch + k] & mask;
+        if (!nz(cand)) continue;
+        int cs[DV];
+        load_row<DV>(vn_cn + (size_t)a * DV, cs);
+#pragma unroll
+        for (int i = 0; i < DV; i++) cand &= ld_stream(ex2 + (size_t)cs[i] * ch + k);
+        for (int half = 0; half < 2; half++) {
+            u64 m = half ? cand.y : cand.x;
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const int w = 2 * k + half;
+                int partner = -1; bool ok = true;
+                for (int i = 0; i < DV && ok; i++) {
+                    const int c = cs[i];
+                    for (int j = 0; j < DC; j++) {
+                        const int e = cn_edge[(size_t)c * DC + j];
+                        if (e == p.E) continue;
+                        const int u = e / DV;
+                        if (u == a) continue;
+                        const u64 xw = reinterpret_cast<const u64 *>(x)[((size_t)u * ch) * 2 + w];
+                        if ((xw >> b) & 1ull) { if (partner < 0) partner = u; else if (partner != u) ok = false; }
+                    }
+                }
+                if (ok && partner > a && partner / p.vns_pos == a / p.vns_pos)
+                    atomicAdd(p.pos_pairs + ((size_t)g * p.L + a / p.vns_pos) * p.lanes + w * 64 + b, 1);
+            }
+        }
+    }
+}
+
 
 __global__ void bp_lane_final_kernel(BpParams p, BpFinalOut o)
 {
@@ -594,10 +668,16 @@ static void launch_count_pairs(const BpParams &p, cudaStream_t st)
 {
     int bx = (p.vns_pos * p.chunks + 255) / 256;
     if (bx > 8) bx = 8;
-    g_prof.launches += 2;
     bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
     dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, 4);
-    bp_pairs_kernel<DV, DC><<<gp, 256, 0, st>>>(p);
+    if (p.ex2 && p.lane_mask) {
+        g_prof.launches += 3;
+        bp_ex2_kernel<DV, DC><<<sweep_grid((long long)p.nk << p.chunk_shift, p.G, 256, 4), 256, 0, st>>>(p);
+        bp_pairs2_kernel<DV, DC><<<gp, 256, 0, st>>>(p);
+    } else {
+        g_prof.launches += 2;
+        bp_pairs_kernel<DV, DC><<<gp, 256, 0, st>>>(p);
+    }
 }
 
 // erased VNs per (position, lane) and accepted size-two stopping sets, restricted to p.lane_mask

@@ -17,6 +17,8 @@
 // L2 across iterations, so most of its traffic never reaches HBM.
 //
 // Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
+#include <climits>
+
 #include "common.cuh"
 
 namespace scldpc {
@@ -510,32 +512,62 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
     }
     __syncthreads();
     const int next0 = p.next_frame[g];
+    // frames that stopped with erased VNs left (fail_mask): one warp per frame sums the per-position counts; every other
+    // frame's counts are zero by construction
+    for (int l = threadIdx.x >> 5; l < p.lanes; l += blockDim.x >> 5) {
+        const int w = l >> 6, b = l & 63;
+        if (!((s_done[w] >> b) & 1ull) || !((p.fail_mask[g * W + w] >> b) & 1ull)) continue;
+        const int fr = p.lane_frame[g * p.lanes + l];
+        int residual = 0, blocks = 0, e_exp = 0, b_exp = 0, first_q = INT_MAX, first_ex = 0;
+        for (int q = threadIdx.x & 31; q < L; q += 32) {
+            const size_t o = ((size_t)g * L + q) * p.lanes + l;
+            const int plain = p.pos_cnt[o], ex = plain - 2 * p.pos_pairs[o];
+            if (plain) p.pos_cnt[o] = 0;
+            if (plain != ex) p.pos_pairs[o] = 0;
+            residual += plain;
+            if (plain > 0) blocks++;
+            if (ex > 0) {
+                e_exp += ex; b_exp++;
+                if (first_q == INT_MAX) { first_q = q; first_ex = ex; }     // q ascends within a thread
+            }
+        }
+        if (!exp_all) {                                          // decodeBP adds only the first such position (BP_FULL.c:1126-1131)
+            int fq = first_q;
+            for (int o = 16; o; o >>= 1) fq = min(fq, __shfl_xor_sync(0xffffffffu, fq, o));
+            e_exp = (fq != INT_MAX && first_q == fq) ? first_ex : 0;
+            b_exp = (fq != INT_MAX && first_q == fq) ? 1 : 0;
+        }
+        for (int o = 16; o; o >>= 1) {
+            residual += __shfl_xor_sync(0xffffffffu, residual, o);
+            blocks += __shfl_xor_sync(0xffffffffu, blocks, o);
+            e_exp += __shfl_xor_sync(0xffffffffu, e_exp, o);
+            b_exp += __shfl_xor_sync(0xffffffffu, b_exp, o);
+        }
+        if ((threadIdx.x & 31) == 0 && fr >= 0 && fr < B) {
+            const size_t o = (size_t)g * B + fr;
+            p.s_residual[o] = residual;
+            p.s_blocks_err[o] = blocks;
+            p.s_erasures_exp[o] = e_exp;
+            p.s_blocks_err_exp[o] = b_exp;
+        }
+    }
+    __syncthreads();
     for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
         const int w = l >> 6, b = l & 63;
         if (!((s_done[w] >> b) & 1ull)) continue;
         const int fr = p.lane_frame[g * p.lanes + l];
-        int residual = 0, blocks = 0, e_exp = 0, b_exp = 0, first_done = 0;
-        // only frames that stopped with erased VNs left were counted (fail_mask): every other frame's results are zero
-        if ((p.fail_mask[g * W + w] >> b) & 1ull)
-            for (int q = 0; q < L; q++) {
-                const size_t o = ((size_t)g * L + q) * p.lanes + l;
-                const int plain = p.pos_cnt[o], ex = plain - 2 * p.pos_pairs[o];
-                if (plain) p.pos_cnt[o] = 0;
-                if (plain != ex) p.pos_pairs[o] = 0;
-                residual += plain;
-                if (plain > 0) blocks++;
-                if (ex > 0 && (exp_all || !first_done)) { first_done = 1; e_exp += ex; b_exp++; }
-            }
         if (fr >= 0 && fr < B) {
             const size_t o = (size_t)g * B + fr;
             const int its = p.lane_iter[g * p.lanes + l];
             p.s_iters[o] = its;
             atomicAdd(&s_frames, 1);
             atomicAdd(&s_its, (unsigned long long)its);
-            p.s_residual[o] = residual;
-            p.s_blocks_err[o] = blocks;
-            p.s_erasures_exp[o] = e_exp;
-            p.s_blocks_err_exp[o] = b_exp;
+            if (!((p.fail_mask[g * W + w] >> b) & 1ull)) {
+                p.s_residual[o] = 0;
+                p.s_blocks_err[o] = 0;
+                p.s_erasures_exp[o] = 0;
+                p.s_blocks_err_exp[o] = 0;
+            }
         }
         // freed lanes take the next frame ids in ascending lane order
         const int nf = next0 + s_rank[w] + __popcll(s_done[w] & ((1ull << b) - 1ull));

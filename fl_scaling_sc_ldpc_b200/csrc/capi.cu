@@ -160,6 +160,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     if (flags & SCLDPC_F_STREAM) {
         q.x = c.take<u128>(G * n * ch);                               // stream mode owns its decision plane
         q.xb = c.take<u128>(G * n * ch);
+        q.ex2 = c.take<u128>(G * nk * ch);
         q.dirty = c.take<unsigned char>(G * n * ch);
         q.first_new = c.take<u64>(G * W);
     }

@@ -228,6 +228,7 @@ struct BpParams {
     u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested
     u128 *xb;                 // [G][n][chunks] node-state streams: the erased set being built by this iteration's CN sweep (bp_node_kernels.cu)
     unsigned char *dirty;     // [G][n*chunks] node-state streams: rows of xb the CN sweep cleared bits in
+    u128 *ex2;                // [G][nk][chunks] frame streams: "exactly two erased neighbours" plane of the harvest (NULL: one-pass pairs kernel)
     u64 *first_new;           // [G][W] node-state streams: lanes whose new frame has a VN the channel left known
     u64 *fail_mask;           // [G][W] subset of done_mask that stopped with erased VNs left (the only lanes the count kernels read)
     int *lane_frame;          // [G][lanes] frame id decoded in the lane, -1 if idle
