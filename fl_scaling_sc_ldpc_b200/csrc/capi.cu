@@ -527,11 +527,11 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     }
-    // Harvest period: a harvest costs about as much as 3.4 iterations (count / pair kernels, channel draws of the re-armed
-    // lanes) and a finished frame idles H/2 iterations on average, so the best period is about sqrt(7..10 x iterations per
-    // frame).  harvest_every <= 0: adapt it to the frames harvested so far (the slowest graph still decoding); > 0: fixed.
+    // Harvest period: a harvest costs about as much as two to three iterations (count / pair kernels, channel draws of the
+    // re-armed lanes) and a finished frame idles H/2 iterations on average, so the best period is about sqrt(6 x iterations
+    // per frame); measured flat between 3.5 and 10 at M = 10000.  harvest_every <= 0: adapt it to the frames harvested so far (the slowest graph still decoding); > 0: fixed.
     const bool adaptive = cfg->harvest_every <= 0;
-    const int hc10 = env_int("SCLDPC_HARVEST_C10", 100, 1, 1000);
+    const int hc10 = env_int("SCLDPC_HARVEST_C10", 60, 1, 1000);
     int H = adaptive ? 16 : cfg->harvest_every;
     CU(cudaMemsetAsync(p.alive_total + 1, 0, 2 * sizeof(int), st));
     CU(cudaMemsetAsync(p.h_cum, 0, sizeof(long long) * 2 * (size_t)p.G, st));
