@@ -119,6 +119,8 @@ struct Carve {
     }
 };
 
+static int env_int(const char *name, int dflt, int lo, int hi);
+
 static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *p)
 {
     const size_t G = d->n_graphs, W = d->n_words, ch = W / 2, lanes = 64 * W;
@@ -126,8 +128,10 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     Carve c{static_cast<char *>(ws), 0};
     BpParams q;
     memset(&q, 0, sizeof q);
-    q.v2c = c.take<u128>(G * (E + 1) * ch);
-    q.c2v = c.take<u128>(G * nk * d->dc * ch);
+    // frame streams in node-state form (the default, see scldpc_bp_stream) keep no messages: 2 bits per edge less per frame
+    const bool no_msgs = (flags & SCLDPC_F_STREAM) && env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
+    q.v2c = no_msgs ? nullptr : c.take<u128>(G * (E + 1) * ch);
+    q.c2v = no_msgs ? nullptr : c.take<u128>(G * nk * d->dc * ch);
     q.latch = (flags & SCLDPC_F_TRAJECTORY) ? c.take<u128>(G * nk * ch) : nullptr;
     q.active = c.take<u64>(G * W);
     q.any_new = c.take<u64>(G * W);
@@ -142,7 +146,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.pos_cnt = c.take<int>(G * d->L * lanes);
     q.pos_pairs = c.take<int>(G * d->L * lanes);
     q.work = c.take<long long>(G * lanes);
-    q.y = c.take<u128>(G * n * ch);
+    q.y = no_msgs ? nullptr : c.take<u128>(G * n * ch);
     q.pos_er_new = c.take<u64>(G * d->L * W);
     q.vn_stamp = c.take<int>(G * d->L);
     q.cn_list = c.take<int>(G * (d->L + d->dv - 1));
@@ -164,7 +168,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         q.dirty = c.take<unsigned char>(G * n * ch);
         q.first_new = c.take<u64>(G * W);
     }
-    q.cn_dis = c.take<u128>(G * nk * ch);                             // sized for the largest possible ignored head
+    q.cn_dis = (flags & SCLDPC_F_STREAM) ? nullptr : c.take<u128>(G * nk * ch);   // sized for the largest possible ignored head
     if (p) *p = q;
     return c.off;
 }
