@@ -371,6 +371,135 @@ __global__ void __launch_bounds__(256) bp_window_persistent_kernel(BpParams p0, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// window decoder in node-state form (see bp_node_kernels.cu for the formulation).  Two planes per VN and frame:
+//   x  = the state the CNs see (what the VN's outgoing messages say; only changes when the VN is swept), and at the end
+//        the decision recorded when the VN's position was the window's target;
+//   xb = the VN's a-posteriori erasure from everything it has been told so far (channel AND incoming messages), including
+//        by CNs of windows that do not sweep the VN -- the out-of-window messages the reference keeps in Lij.
+// CN sweep over [c0, c1): a CN with exactly one erased neighbour in x clears it in xb (frames that still iterate in this
+// window only: a frame that stopped keeps its state, like FREEZE).  VN sweep over [v0, v1): x := xb, "a decision changed"
+// and "an erased VN is left" for the window-wide stall rule (BP_SW.c:791-816), then the same lane retirement as the message
+// kernels.  Checked bit for bit against the message kernels, the oracle and the compiled decodeBP_SW (tests/test_bp_parity_gpu.py:
+// residual, P1, blocks, expurgated counts, erased VNs; 1920 random cases of a numpy restatement incl. per-window iterations).
+// ------------------------------------------------------------------------------------------------------------
+template <int DV, int DC>
+__global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
+{
+    static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    if (!nz(act)) return;                                       // a thread keeps its chunk
+    const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
+    unsigned *__restrict__ xbk = reinterpret_cast<unsigned *>(p.xb + (size_t)g * p.n * ch + k);
+    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const int items = (p.c1 - p.c0) << p.chunk_shift;
+    const int stride = gridDim.x * blockDim.x;
+    const int E = p.E;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+        const int32_t *row = cn_edge + (size_t)(p.c0 + (idx >> p.chunk_shift)) * DC;
+        int e[DC];
+        load_row<DC>(row, e);
+        u128 in[DC];
+#pragma unroll
+        for (int j = 0; j < DC; j++) in[j] = (e[j] != E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
+        u128 one = zero128(), tw = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
+#pragma unroll
+        for (int j = 0; j < DC; j++) {
+            tw |= one & in[j];
+            one |= in[j];
+            if (j & 1) b0 |= in[j];
+            if (j & 2) b1 |= in[j];
+            if (j & 4) b2 |= in[j];
+            if (j & 8) b3 |= in[j];
+        }
+        const u128 res = one & ~tw & act;                       // exactly one erased neighbour, frame still iterating
+        if (nz(res)) {
+            const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
+            const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
+            const unsigned w1[4] = {(unsigned)b1.x, (unsigned)(b1.x >> 32), (unsigned)b1.y, (unsigned)(b1.y >> 32)};
+            const unsigned w2[4] = {(unsigned)b2.x, (unsigned)(b2.x >> 32), (unsigned)b2.y, (unsigned)(b2.y >> 32)};
+            const unsigned w3[4] = {(unsigned)b3.x, (unsigned)(b3.x >> 32), (unsigned)b3.y, (unsigned)(b3.y >> 32)};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                unsigned m = rw[q];
+                while (m) {
+                    const int b = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
+                    if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
+                    const unsigned o = (unsigned)((__ldg(row + j) / DV) << p.chunk_shift);
+                    atomicAnd(xbk + 4 * (size_t)o + q, ~(1u << b));
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) bpw_vn_node_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
+    __shared__ int s_last;
+    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_new[threadIdx.x] = 0; s_er[threadIdx.x] = 0; }
+    __syncthreads();
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    u128 acc_new = zero128(), acc_er = zero128();
+    u128 *__restrict__ x = p.x + ((size_t)g * p.n + p.v0) * ch;
+    const u128 *__restrict__ xb = p.xb + ((size_t)g * p.n + p.v0) * ch;
+    const int items = (p.v1 - p.v0) << p.chunk_shift;
+    const int stride = gridDim.x * blockDim.x;
+    if (nz(act))
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
+            const u128 xo = x[idx];
+            const u128 xn = sel(act, ld_cg128(xb + idx), xo);  // the CN sweep wrote xb with atomics (L2)
+            if (neq(xn, xo)) x[idx] = xn;
+            // a window's first iteration compares with NumErasuresPrecTerm = n: "progress" = some VN of the range is known
+            acc_new |= (p.first_iter ? ~xn : (xo & ~xn)) & act;
+            acc_er |= xn & act;
+        }
+    acc_new = warp_or_same_chunk(acc_new, ch);
+    acc_er = warp_or_same_chunk(acc_er, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
+        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
+        if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
+        if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
+        if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        bp_retire_lanes<false>(p, g);
+    }
+}
+
+// x = xb = channel erasures (Lji = channel value on every edge, Lij = 1: BP_SW.c:650-659)
+__global__ void bpw_node_init_kernel(BpParams p)
+{
+    const size_t items = (size_t)p.G * p.n * p.chunks;
+    const u128 *chan = reinterpret_cast<const u128 *>(p.chan);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (size_t)gridDim.x * blockDim.x) {
+        const u128 c = chan[i];
+        p.x[i] = c;
+        p.xb[i] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // finalisation: per-position erasure counts, size-two stopping sets, per-frame results
 // ------------------------------------------------------------------------------------------------------------
 // grid (blocks per position, L, G): erased VNs per (position, lane)
@@ -597,6 +726,34 @@ static void launch_iteration(const BpParams &p, bool traj, bool freeze, cudaStre
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
     }
+}
+
+template <int DV, int DC>
+static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int blocks_per_sm)
+{
+    const int block = 256;
+    dim3 gc = sweep_grid((long long)(p.c1 - p.c0) << p.chunk_shift, p.G, block, blocks_per_sm);
+    dim3 gv = sweep_grid((long long)(p.v1 - p.v0) << p.chunk_shift, p.G, block, blocks_per_sm);
+    g_prof.launches += (p.c1 > p.c0) ? 2 : 1;
+    if (p.c1 > p.c0) bpw_cn_node_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    bpw_vn_node_kernel<<<gv, block, 0, st>>>(p);
+}
+
+int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm)
+{
+    if (dv == 4 && dc == 8) launch_window_node_iteration<4, 8>(p, st, blocks_per_sm);
+    else if (dv == 3 && dc == 6) launch_window_node_iteration<3, 6>(p, st, blocks_per_sm);
+    else if (dv == 5 && dc == 10) launch_window_node_iteration<5, 10>(p, st, blocks_per_sm);
+    else if (dv == 3 && dc == 9) launch_window_node_iteration<3, 9>(p, st, blocks_per_sm);
+    else if (dv == 4 && dc == 12) launch_window_node_iteration<4, 12>(p, st, blocks_per_sm);
+    else return -1;
+    return 0;
+}
+
+void bp_launch_window_node_init(const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    bpw_node_init_kernel<<<num_sms() * 8, 256, 0, st>>>(p);
 }
 
 template <int DV, int DC>

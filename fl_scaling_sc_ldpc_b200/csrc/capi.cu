@@ -23,6 +23,8 @@ int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaS
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
 int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
 int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
+int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
+void bp_launch_window_node_init(const BpParams &p, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
 int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
@@ -353,7 +355,8 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 // frame; after each chunk that counter is copied to pinned host memory and the NEXT chunk is enqueued before the
 // host waits for the copy, so the GPU never idles on the host.  Sweeps of a finished graph return at once, so the
 // overshoot (at most two chunks) costs launch latency only.
-static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool freeze, bool wave, cudaStream_t st, int *launched)
+static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool freeze, bool wave, cudaStream_t st, int *launched,
+                          bool window_node = false)
 {
     int *hf = nullptr, rc;
     if ((rc = host_flag(&hf))) return rc;
@@ -374,7 +377,8 @@ static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool 
             p->max_it = cap;
             p->first_iter = (it == 0);
             p->row = traj ? it : -1;
-            if (wave ? bp_launch_wave_iteration(dv, dc, *p, traj, st, waves) : bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps))
+            if (window_node ? bp_launch_window_node_iteration(dv, dc, *p, st, bps)
+                            : (wave ? bp_launch_wave_iteration(dv, dc, *p, traj, st, waves) : bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps)))
                 return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
         CU(cudaGetLastError());
@@ -590,13 +594,22 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
     const int ms = d->dv - 1, L = d->L, vp = d->vns_pos, cp = d->cns_pos;
     const int nwin = square ? L : L + ms;                          // BP_SW.c:672 / BP_FULL.c:668
     const int cn_clip = term ? p.nk : L * cp;
-    bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
-    CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
+    // SCLDPC_WINDOW_NODE=0 selects the message-passing sweeps (the implementation of record); the default is their node-state
+    // form (bpw_*_node_kernel in bp_kernels.cu): same decisions, counters and per-window stopping, about a third of the traffic
+    const bool node = env_int("SCLDPC_WINDOW_NODE", 1, 0, 1) != 0 && d->n_frames > 0;
+    if (node) {
+        p.xb = p.y;                                                // the wave-tracking plane is free in window mode
+        bp_launch_init_ctrl_only(p, d->n_frames, st);
+        bp_launch_window_node_init(p, st);
+    } else {
+        bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
+        CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
+    }
     CU(cudaGetLastError());
     // Opt-in (SCLDPC_PERSISTENT=1): measured on B200 the cooperative kernel is 15-25 % SLOWER than two launches per
     // iteration (W=3: 81 vs 70 ms, W=10: 275 vs 215 ms for 4 graphs x 1024 frames, L=100, M=10000) -- three grid-wide
     // syncs per iteration and 2 instead of 3-4 resident blocks per SM cost more than the launches they replace.
-    bool persistent = env_int("SCLDPC_PERSISTENT", 0, 0, 1) != 0;
+    bool persistent = !node && env_int("SCLDPC_PERSISTENT", 0, 0, 1) != 0;
     for (int posW = 0; posW < nwin && d->n_frames > 0; posW++) {
         long long c0 = (long long)posW * cp, c1 = c0 + (long long)W * cp;
         if (c1 > cn_clip) c1 = cn_clip;
@@ -623,7 +636,7 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
         if (prc == -1) return fail(SCLDPC_EINVAL, "unsupported degrees");
         if (prc == -2) {
             persistent = false;
-            if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr))) return rc;
+            if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr, node))) return rc;
         }
     }
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,

@@ -99,9 +99,11 @@ def test_full_bp_extreme_channels():
         check_bp(eng.decode_bp_full(fb, 0, is_term, trajectory=True, max_rows=32), ref, rows=True)
 
 
-@pytest.fixture(params=["two_launches", "persistent"])
+@pytest.fixture(params=["node_state", "two_launches", "persistent"])
 def window_mode(request, monkeypatch):
-    """the window decoder as two launches per iteration (default) and as one cooperative launch per window"""
+    """the window decoder in node-state form (default), with message-passing sweeps as two launches per iteration, and
+    with message-passing sweeps as one cooperative launch per window"""
+    monkeypatch.setenv("SCLDPC_WINDOW_NODE", "1" if request.param == "node_state" else "0")
     if request.param == "persistent":
         monkeypatch.setenv("SCLDPC_PERSISTENT", "1")
     else:
