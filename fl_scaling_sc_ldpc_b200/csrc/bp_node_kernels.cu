@@ -10,8 +10,8 @@
 // reference's stall rule (NumErasures == NumErasuresPrec, BP_FULL.c:1046-1066), the error counts and the expurgation
 // inputs -- is bit-identical to decodeBP's at every iteration; tests/test_stream_gpu.py holds it against the message
 // kernels (themselves checked against the oracle and the compiled reference).  What the formulation does not carry are
-// the messages, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) and the window decoders stay on the message
-// kernels (bp_kernels.cu / bp_wave_kernels.cu), which remain the implementation of record.
+// the messages, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) stays on the message kernels (bp_kernels.cu /
+// bp_wave_kernels.cu), which remain the implementation of record; the window decoder's node-state form is in bp_kernels.cu.
 //
 // State per graph: x and xb [n][chunks] (1 bit per VN and frame; equal between iterations).
 //   CN sweep  : gathers the dc x rows of a CN (E rows through L2: the gather stays inside a band of dv positions, 5 MB at
