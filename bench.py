@@ -311,7 +311,8 @@ def run_ours(args):
         fi_per_launch = local_frame_iters / max(1, n_iter_launches)
         cn_bytes = fi_per_launch * (2 * E_EDGES) / 8.0
         vn_bytes = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
-        node_state = stream_mode and os.environ.get("SCLDPC_STREAM_NODE", "1") != "0"
+        node_state = os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") != "0"
+        k_cn, k_x = ("ns_cn_kernel<4,8>", "ns_x_kernel") if stream_mode else ("bpw_cn_node_kernel<4,8>", "bpw_vn_node_kernel")
         tj = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
@@ -326,9 +327,9 @@ def run_ours(args):
             # node-state minimum (2n+nk)/8 are reported next to it, so a fraction above 1 is explained, not hidden.
             it_bytes = fi_per_launch * (4 * E_EDGES + N_VNS) / 8.0
             ach = it_bytes / (cn_avg + vn_avg) / 1e9
-            tn = tj.get("node_state", {})
+            tn = tj.get("node_state", {}) if stream_mode else {}
             traffic = tn.get("iteration_dram_bytes_per_launch")
-            roof = {"bound": "hbm", "kernel": "ns_cn_kernel<4,8> + ns_x_kernel (one flooding iteration)", "achieved": ach, "peak": peak,
+            roof = {"bound": "hbm", "kernel": k_cn + " + " + k_x + " (one flooding iteration)", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "traffic_note": tn.get("note"), "peak_source": peak_src, "launches_sampled": n_s,
                     "avg_launch_ms": 1e3 * (cn_avg + vn_avg), "frame_iterations_per_launch": fi_per_launch,
@@ -339,10 +340,10 @@ def run_ours(args):
                                    "The kernels are bound by L2->SM sector bandwidth: see l2 below",
                     "l2": {"bytes_per_launch": tn.get("cn_l2_read_bytes_per_launch"), "note": tn.get("l2_note")}}
             pct = lambda a, q: float(np.percentile(np.asarray(a[:n_s], dtype=np.float64), q))
-            kernels = {"ns_cn_kernel<4,8>": {"avg_launch_ms": 1e3 * cn_avg, "p10_p50_p90_ms": [pct(cn_ms, 10), pct(cn_ms, 50), pct(cn_ms, 90)],
+            kernels = {k_cn: {"avg_launch_ms": 1e3 * cn_avg, "p10_p50_p90_ms": [pct(cn_ms, 10), pct(cn_ms, 50), pct(cn_ms, 90)],
                                              "share_of_iteration": cn_avg / (cn_avg + vn_avg),
                                              "dram_bytes_per_launch": tn.get("cn_dram_bytes_per_launch")},
-                       "ns_x_kernel": {"avg_launch_ms": 1e3 * vn_avg, "p10_p50_p90_ms": [pct(vn_ms, 10), pct(vn_ms, 50), pct(vn_ms, 90)],
+                       k_x: {"avg_launch_ms": 1e3 * vn_avg, "p10_p50_p90_ms": [pct(vn_ms, 10), pct(vn_ms, 50), pct(vn_ms, 90)],
                                        "share_of_iteration": vn_avg / (cn_avg + vn_avg),
                                        "dram_bytes_per_launch": tn.get("x_dram_bytes_per_launch")}}
         else:
@@ -420,7 +421,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (64 bit-sliced frames per word)", "data": "synthetic",
-            "config": {"workload": WORKLOAD.replace("B frames", f"{B} frames"), "mode": args.mode, "sweeps": ("node-state (bp_node_kernels.cu)" if (stream_mode and os.environ.get("SCLDPC_STREAM_NODE", "1") != "0") else "message passing"), "frames_per_step_per_gpu": G * B,
+            "config": {"workload": WORKLOAD.replace("B frames", f"{B} frames"), "mode": args.mode, "sweeps": ("node-state" if os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") != "0" else "message passing"), "frames_per_step_per_gpu": G * B,
                        "lanes_per_graph": lanes, "n_words": N_WORDS,
                        "l2": f"inputs larger than L2: {ws_mb:.0f} MB of decoder state per batch, two batches alternated",
                        "seed": args.seed},

@@ -734,9 +734,17 @@ static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int
     const int block = 256;
     dim3 gc = sweep_grid((long long)(p.c1 - p.c0) << p.chunk_shift, p.G, block, blocks_per_sm);
     dim3 gv = sweep_grid((long long)(p.v1 - p.v0) << p.chunk_shift, p.G, block, blocks_per_sm);
+    const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
+    cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
+    if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += (p.c1 > p.c0) ? 2 : 1;
     if (p.c1 > p.c0) bpw_cn_node_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    if (sample) cudaEventRecord(ev[1], st);
     bpw_vn_node_kernel<<<gv, block, 0, st>>>(p);
+    if (sample) {
+        cudaEventRecord(ev[2], st);
+        g_prof.iter_idx[g_prof.n_samples++] = p.iter;
+    }
 }
 
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm)

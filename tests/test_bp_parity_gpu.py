@@ -33,10 +33,12 @@ def check_bp(res, ref, rows=False):
                 assert (res.rows[g, f, :k] == ref["rows"][g, f, :k]).all(), (g, f)
 
 
-@pytest.fixture(params=["wave", "sweep_all"])
+@pytest.fixture(params=["node_state", "wave", "sweep_all"])
 def sweep_mode(request, monkeypatch):
-    """full BP runs with wave tracking (only positions whose inputs changed are swept) and with every position swept
-    in every iteration, like the reference; both must be bit-identical to the oracle"""
+    """full BP in node-state form (default for runs without a trajectory), with message passing and wave tracking (only
+    positions whose inputs changed are swept), and with message passing over every position in every iteration, like the
+    reference; all must be bit-identical to the oracle.  Trajectory runs always pass messages."""
+    monkeypatch.setenv("SCLDPC_FULL_NODE", "1" if request.param == "node_state" else "0")
     if request.param == "sweep_all":
         monkeypatch.setenv("SCLDPC_NO_WAVE", "1")
     else:

@@ -17,7 +17,20 @@ def stream_kernels(request, monkeypatch):
 
 
 def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
-    """frames 0..B-1 decoded 128 at a time with the synchronous decoder on the same graphs"""
+    """frames 0..B-1 decoded 128 at a time with the synchronous message-passing decoder on the same graphs"""
+    import os
+    old = os.environ.get("SCLDPC_FULL_NODE")
+    os.environ["SCLDPC_FULL_NODE"] = "0"
+    try:
+        return _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping)
+    finally:
+        if old is None:
+            del os.environ["SCLDPC_FULL_NODE"]
+        else:
+            os.environ["SCLDPC_FULL_NODE"] = old
+
+
+def _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
     G = fb_graphs.n_graphs
     out = {k: np.zeros((G, B), np.int32) for k in KEYS}
     for f0 in range(0, B, 128):
