@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) bp_window_persistent_kernel(BpParams p0, 
 // kernels.  Checked bit for bit against the message kernels, the oracle and the compiled decodeBP_SW (tests/test_bp_parity_gpu.py:
 // residual, P1, blocks, expurgated counts, erased VNs; 1920 random cases of a numpy restatement incl. per-window iterations).
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, int DC>
+template <int DV, int DC, bool HEAD>
 __global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
@@ -415,7 +415,17 @@ __global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
             if (j & 4) b2 |= in[j];
             if (j & 8) b3 |= in[j];
         }
-        const u128 res = one & ~tw & act;                       // exactly one erased neighbour, frame still iterating
+        u128 res = one & ~tw & act;                             // exactly one erased neighbour, frame still iterating
+        if (HEAD && p.c0 + (idx >> p.chunk_shift) < p.cn_dis_lim) {
+            // Unscanned head of simulate_sc_ldpc (is_bounded = False): a slot below the scan start is only decoded when a
+            // removal leaves it with one user (PD.py:308-311), so a CN that starts with exactly one erased neighbour never
+            // resolves it (same plane as bp_cn_wave_kernel<.,.,HEAD>)
+            u128 *dp = p.cn_dis + ((size_t)g * p.cn_dis_lim + p.c0 + (idx >> p.chunk_shift)) * ch + k;
+            u128 dis;
+            if (p.first_iter) { dis = one & ~tw; *dp = dis; }
+            else dis = *dp;
+            res &= ~dis;
+        }
         if (nz(res)) {
             const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
             const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
@@ -738,7 +748,10 @@ static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += (p.c1 > p.c0) ? 2 : 1;
-    if (p.c1 > p.c0) bpw_cn_node_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    if (p.c1 > p.c0) {
+        if (p.cn_dis_lim > 0) bpw_cn_node_kernel<DV, DC, true><<<gc, block, 0, st>>>(p);
+        else bpw_cn_node_kernel<DV, DC, false><<<gc, block, 0, st>>>(p);
+    }
     if (sample) cudaEventRecord(ev[1], st);
     bpw_vn_node_kernel<<<gv, block, 0, st>>>(p);
     if (sample) {

@@ -419,10 +419,10 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool traj = flags & SCLDPC_F_TRAJECTORY, term = flags & SCLDPC_F_TERMINATED;
     const int cap = max_it <= 0 ? INT_MAX : max_it;
-    // Error-rate runs (no trajectory, no unscanned head) decode in node-state form: the window kernels of bp_kernels.cu with
+    // Error-rate runs (no trajectory) decode in node-state form: the window kernels of bp_kernels.cu with
     // one window that covers the whole code -- same erased set and stopping at every iteration as the message kernels,
     // which SCLDPC_FULL_NODE=0 selects and which trajectory mode always uses.
-    const bool node = !traj && g_unscanned_cns == 0 && d->n_frames > 0 && env_int("SCLDPC_FULL_NODE", 1, 0, 1) != 0;
+    const bool node = !traj && d->n_frames > 0 && env_int("SCLDPC_FULL_NODE", 1, 0, 1) != 0;
     if (node) {
         p.xb = p.y;
         bp_launch_init_ctrl_only(p, d->n_frames, st);
@@ -439,7 +439,7 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     // wave tracking (bp_wave_kernels.cu) unless disabled or the chain is longer than its shared-memory bitmaps
     const bool wave = !node && d->L + d->dv - 1 <= 1024 && (!env_int("SCLDPC_NO_WAVE", 0, 0, 1) || g_unscanned_cns > 0);
     p.cn_dis_lim = g_unscanned_cns;
-    if (g_unscanned_cns > 0 && (!wave || traj || g_unscanned_cns > p.nk))
+    if (g_unscanned_cns > 0 && ((!wave && !node) || traj || g_unscanned_cns > p.nk))
         return fail(SCLDPC_EINVAL, "unscanned head: not available with trajectories or for this chain length");
     p.cn_pos_lim = term ? d->L + d->dv - 1 : d->L;
     if (wave) bp_launch_wave_init(p, st);
