@@ -464,14 +464,27 @@ __global__ void __launch_bounds__(256, 4) bpw_vn_node_kernel(BpParams p)
     const u128 *__restrict__ xb = p.xb + ((size_t)g * p.n + p.v0) * ch;
     const int items = (p.v1 - p.v0) << p.chunk_shift;
     const int stride = gridDim.x * blockDim.x;
+    constexpr int U = 4;                                        // rows in flight per thread: a plain stream, latency-bound otherwise
     if (nz(act))
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
-            const u128 xo = x[idx];
-            const u128 xn = sel(act, ld_cg128(xb + idx), xo);  // the CN sweep wrote xb with atomics (L2)
-            if (neq(xn, xo)) x[idx] = xn;
-            // a window's first iteration compares with NumErasuresPrecTerm = n: "progress" = some VN of the range is known
-            acc_new |= (p.first_iter ? ~xn : (xo & ~xn)) & act;
-            acc_er |= xn & act;
+        for (int base = blockIdx.x * blockDim.x * U + threadIdx.x; base < items; base += stride * U) {
+            u128 xos[U], xbs[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int idx = base + u * (int)blockDim.x;
+                xos[u] = zero128(); xbs[u] = zero128();
+                if (idx < items) { xos[u] = x[idx]; xbs[u] = ld_cg128(xb + idx); }   // the CN sweep wrote xb with atomics (L2)
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int idx = base + u * (int)blockDim.x;
+                if (idx >= items) break;
+                const u128 xo = xos[u];
+                const u128 xn = sel(act, xbs[u], xo);
+                if (neq(xn, xo)) x[idx] = xn;
+                // a window's first iteration compares with NumErasuresPrecTerm = n: "progress" = some VN of the range is known
+                acc_new |= (p.first_iter ? ~xn : (xo & ~xn)) & act;
+                acc_er |= xn & act;
+            }
         }
     acc_new = warp_or_same_chunk(acc_new, ch);
     acc_er = warp_or_same_chunk(acc_er, ch);
@@ -743,7 +756,7 @@ static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int
 {
     const int block = 256;
     dim3 gc = sweep_grid((long long)(p.c1 - p.c0) << p.chunk_shift, p.G, block, blocks_per_sm);
-    dim3 gv = sweep_grid((long long)(p.v1 - p.v0) << p.chunk_shift, p.G, block, blocks_per_sm);
+    dim3 gv = sweep_grid((((long long)(p.v1 - p.v0) << p.chunk_shift) + 3) / 4, p.G, block, blocks_per_sm);   // four rows per thread and trip
     const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
