@@ -21,11 +21,35 @@
 // frame-iteration (158 KB measured against 148 KB) instead of (4E + n)/8 = 1062 KB.
 //
 // Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scldpc {
 
 constexpr int NS_X_ROWS = 4;
+
+// Programmatic dependent launch: the two kernels of an iteration follow each other ~10^5 times per decode, so the launch
+// gap between them is worth hiding.  Every block first waits for the predecessor grid (nothing it wrote is read before
+// that), then lets the successor's blocks be scheduled as soon as all blocks of this grid have started; those blocks sit
+// in their own griddepcontrol.wait until this grid has completed and flushed.
+__device__ __forceinline__ void pdl_wait_then_release()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
@@ -40,6 +64,7 @@ template <int DV, int DC>
 __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
+    pdl_wait_then_release();
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
@@ -118,6 +143,7 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 template <bool ARM>
 __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
 {
+    pdl_wait_then_release();
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
@@ -272,10 +298,12 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += 2;
-    ns_cn_kernel<DV, DC><<<gc, block, 0, st>>>(p);
+    static const bool pdl = getenv("SCLDPC_NO_PDL") == nullptr;
+    // the first launch after a harvest (arm) follows ordinary kernels: full serialisation there
+    launch_pdl(ns_cn_kernel<DV, DC>, gc, dim3(block), st, pdl && !arm && !sample, p);
     if (sample) cudaEventRecord(ev[1], st);
-    if (arm) ns_x_kernel<true><<<gx, block, 0, st>>>(p);
-    else ns_x_kernel<false><<<gx, block, 0, st>>>(p);
+    if (arm) launch_pdl(ns_x_kernel<true>, gx, dim3(block), st, pdl && !sample, p);
+    else launch_pdl(ns_x_kernel<false>, gx, dim3(block), st, pdl && !sample, p);
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
