@@ -20,6 +20,8 @@
 // monotone, so equal counts <=> no VN resolved) or the iteration cap (BP_FULL.c:1044-1065).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scldpc {
@@ -386,6 +388,7 @@ template <int DV, int DC, bool HEAD>
 __global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
+    pdl_wait_then_release();
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     const int ch = p.chunks;
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
 
 __global__ void __launch_bounds__(256, 4) bpw_vn_node_kernel(BpParams p)
 {
+    pdl_wait_then_release();
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
@@ -761,12 +765,15 @@ static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
     g_prof.launches += (p.c1 > p.c0) ? 2 : 1;
+    // programmatic dependent launches inside a window / a call; its first kernel follows ordinary ones
+    static const bool pdl_on = getenv("SCLDPC_NO_PDL") == nullptr;
+    const bool pdl = pdl_on && !sample;
     if (p.c1 > p.c0) {
-        if (p.cn_dis_lim > 0) bpw_cn_node_kernel<DV, DC, true><<<gc, block, 0, st>>>(p);
-        else bpw_cn_node_kernel<DV, DC, false><<<gc, block, 0, st>>>(p);
+        if (p.cn_dis_lim > 0) launch_pdl(bpw_cn_node_kernel<DV, DC, true>, gc, dim3(block), st, pdl && !p.first_iter, p);
+        else launch_pdl(bpw_cn_node_kernel<DV, DC, false>, gc, dim3(block), st, pdl && !p.first_iter, p);
     }
     if (sample) cudaEventRecord(ev[1], st);
-    bpw_vn_node_kernel<<<gv, block, 0, st>>>(p);
+    launch_pdl(bpw_vn_node_kernel, gv, dim3(block), st, pdl && (p.c1 > p.c0 || !p.first_iter), p);
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;

@@ -275,6 +275,29 @@ struct PeelParams {
     uint64_t seed, first_frame;
 };
 
+// Programmatic dependent launch: the two node-state kernels of an iteration follow each other ~10^5 times per decode, so the launch
+// gap between them is worth hiding.  Every block first waits for the predecessor grid (nothing it wrote is read before
+// that), then lets the successor's blocks be scheduled as soon as all blocks of this grid have started; those blocks sit
+// in their own griddepcontrol.wait until this grid has completed and flushed.
+__device__ __forceinline__ void pdl_wait_then_release()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+
 namespace scldpc {
 // host-side instrumentation shared by the launchers (capi.cu owns the storage)
 struct Profiler {
