@@ -54,7 +54,7 @@ class StreamCfg(ctypes.Structure):
     _fields_ = [("frames_per_graph", ctypes.c_int32), ("harvest_every", ctypes.c_int32), ("flags", ctypes.c_uint32),
                 ("n_doped", ctypes.c_int32), ("n_soft", ctypes.c_int32), ("eps_host", ctypes.c_void_p),
                 ("doped_pos_host", ctypes.c_void_p), ("soft_pos_host", ctypes.c_void_p), ("soft_count_host", ctypes.c_void_p),
-                ("seed", ctypes.c_uint64), ("first_graph_id", ctypes.c_uint64)]
+                ("seed", ctypes.c_uint64), ("first_graph_id", ctypes.c_uint64), ("max_it", ctypes.c_int32)]
 
 
 class StreamOut(ctypes.Structure):

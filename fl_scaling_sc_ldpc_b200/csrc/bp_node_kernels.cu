@@ -38,7 +38,9 @@ constexpr int NS_X_ROWS = 4;
 // registers (-2 %).  The index of the neighbour to clear is carried in bit planes next to the saturating count, which
 // keeps the divergent scatter at ~30 instructions per resolution.
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, int DC>
+// CAPPED (streams with an iteration cap): a frame that hit the cap is not at a fixed point, so its bits must not be cleared
+// while it waits for the harvest -- the resolutions are masked with the frames still iterating.
+template <int DV, int DC, bool CAPPED>
 __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
     __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
-    const bool lane_work = nz(reinterpret_cast<const u128 *>(p.active)[g * ch + k]);   // a thread keeps its chunk
+    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
+    const bool lane_work = nz(act);                             // a thread keeps its chunk
     const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
     unsigned *__restrict__ xbk = reinterpret_cast<unsigned *>(p.xb + (size_t)g * p.n * ch + k);
     unsigned char *__restrict__ dirtyk = p.dirty + (size_t)g * p.n * ch + k;
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
                 if (j & 4) b2 |= in[j];
                 if (j & 8) b3 |= in[j];
             }
-            const u128 res = one & ~tw;                         // frames in which exactly one neighbour of c is erased
+            u128 res = one & ~tw;                               // frames in which exactly one neighbour of c is erased
+            if (CAPPED) res &= act;
             if (nz(res)) {
                 acc_new |= res;
                 const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
 // state pass + end of the iteration (last block): brings x up to xb on the rows the CN sweep touched, collects "an erased
 // VN is left", arms freed lanes with their new frames' channel draws; same control flow as bp_vn_stream_kernel
 // ------------------------------------------------------------------------------------------------------------
-template <bool ARM>
+template <bool ARM, bool CAPPED>
 __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
 {
     pdl_wait_then_release();
@@ -214,30 +218,35 @@ __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
     if (!s_last) return;
     __threadfence();
     // ---- end of the iteration for graph g ----
-    __shared__ u64 s_act[SCLDPC_MAX_WORDS];
+    __shared__ u64 s_act[SCLDPC_MAX_WORDS], s_cap[SCLDPC_MAX_WORDS];
     const int W = p.W;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) { s_act[w] = p.active[g * W + w]; s_cap[w] = 0; }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_act[w] >> b) & 1ull) {
+            const int li = p.lane_iter[g * p.lanes + l] + 1;
+            p.lane_iter[g * p.lanes + l] = li;
+            if (CAPPED && li >= p.stream_cap) atomicOr(reinterpret_cast<unsigned long long *>(&s_cap[w]), 1ull << b);   // while (iter < MaxNumIt)
+        }
+    }
+    __syncthreads();
     for (int w = threadIdx.x; w < W; w += blockDim.x) {
         const u64 er = ld_cg(p.any_er + g * W + w);
         p.any_er[g * W + w] = 0;
-        const u64 a = p.active[g * W + w];
+        const u64 a = s_act[w];
         u64 nw = ld_cg(p.any_new + g * W + w);
         if (!ARM) {                                             // lanes armed by the previous pass ran their first iteration
             nw |= ld_cg(p.first_new + g * W + w);
             p.first_new[g * W + w] = 0;
         }
-        const u64 stop = a & (~er | ~nw);                       // NumErasures == 0  ||  == NumErasuresPrec
-        s_act[w] = a;
+        const u64 stop = a & (~er | ~nw | s_cap[w]);            // NumErasures == 0  ||  == NumErasuresPrec  ||  iteration cap
         u64 left = a & ~stop;
         if (ARM) { left |= p.arm_mask[g * W + w]; p.arm_mask[g * W + w] = 0; }   // armed lanes start iterating with the next sweep
         p.active[g * W + w] = left;
         p.done_mask[g * W + w] |= stop;
         p.fail_mask[g * W + w] |= stop & er;
         p.any_new[g * W + w] = 0;
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
-        const int w = l >> 6, b = l & 63;
-        if ((s_act[w] >> b) & 1ull) p.lane_iter[g * p.lanes + l] += 1;
     }
     if (threadIdx.x == 0) p.ticket[g] = 0;
 }
@@ -261,8 +270,8 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
     const int block = 256;
     static int res_cn = 0, res_x = 0;
     if (!res_cn) {
-        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC>, block);
-        res_x = resident_blocks_ns(ns_x_kernel<true>, block);
+        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC, false>, block);
+        res_x = resident_blocks_ns(ns_x_kernel<true, false>, block);
     }
     // every graph gets enough blocks to fill the machine on its own: blocks of finished graphs return at once
     auto grid = [&](int resident, long long items_per_graph) {
@@ -278,10 +287,17 @@ static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
     g_prof.launches += 2;
     static const bool pdl = getenv("SCLDPC_NO_PDL") == nullptr;
     // the first launch after a harvest (arm) follows ordinary kernels: full serialisation there
-    launch_pdl(ns_cn_kernel<DV, DC>, gc, dim3(block), st, pdl && !arm && !sample, p);
+    const bool capped = p.stream_cap > 0;
+    if (capped) launch_pdl(ns_cn_kernel<DV, DC, true>, gc, dim3(block), st, pdl && !arm && !sample, p);
+    else launch_pdl(ns_cn_kernel<DV, DC, false>, gc, dim3(block), st, pdl && !arm && !sample, p);
     if (sample) cudaEventRecord(ev[1], st);
-    if (arm) launch_pdl(ns_x_kernel<true>, gx, dim3(block), st, pdl && !sample, p);
-    else launch_pdl(ns_x_kernel<false>, gx, dim3(block), st, pdl && !sample, p);
+    if (capped) {
+        if (arm) launch_pdl(ns_x_kernel<true, true>, gx, dim3(block), st, pdl && !sample, p);
+        else launch_pdl(ns_x_kernel<false, true>, gx, dim3(block), st, pdl && !sample, p);
+    } else {
+        if (arm) launch_pdl(ns_x_kernel<true, false>, gx, dim3(block), st, pdl && !sample, p);
+        else launch_pdl(ns_x_kernel<false, false>, gx, dim3(block), st, pdl && !sample, p);
+    }
     if (sample) {
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;

@@ -495,6 +495,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     p.c0 = 0; p.c1 = p.cn_pos_lim * d->cns_pos; p.v0 = 0; p.v1 = p.n;
     p.max_it = INT_MAX; p.first_iter = 0; p.stall_at_first = 1;
     p.frames_per_graph = cfg->frames_per_graph; p.seed = cfg->seed; p.first_graph = cfg->first_graph_id;
+    p.stream_cap = cfg->max_it > 0 ? cfg->max_it : 0;
     p.s_iters = out->iters_dev; p.s_residual = out->residual_dev; p.s_blocks_err = out->blocks_err_dev;
     p.s_erasures_exp = out->erasures_exp_dev; p.s_blocks_err_exp = out->blocks_err_exp_dev;
     p.vn_reverse = env_int("SCLDPC_VN_REVERSE", 1, 0, 1);
@@ -518,6 +519,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     // SCLDPC_STREAM_NODE=0 selects the message-passing sweeps (the implementation of record); the default is the node-state
     // formulation of bp_node_kernels.cu, which yields the same erased set at every iteration with ~6x less HBM traffic
     const bool node = env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
+    if (!node && p.stream_cap > 0) return fail(SCLDPC_EINVAL, "capped frame streams need the node-state sweeps (SCLDPC_STREAM_NODE=1)");
     CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
     if (node) {
         CU(cudaMemsetAsync(p.xb, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));

@@ -237,6 +237,7 @@ struct BpParams {
     const u64 *thr;           // [G] erasure threshold eps * 2^32 of the graph's channel
     const int32_t *known;     // [L] doping: the first known[pos] VNs of a position are known (NULL: none)
     int frames_per_graph;     // stream length B
+    int stream_cap;           // frame streams: iteration cap per frame (0: none)
     uint64_t seed, first_graph;
     int *s_iters, *s_residual, *s_blocks_err, *s_erasures_exp, *s_blocks_err_exp;   // [G][B] per-frame results
     // outputs

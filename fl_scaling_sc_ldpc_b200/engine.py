@@ -278,9 +278,9 @@ class StreamResult:
 
 
 def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, first_graph_id: int = 0, is_term: bool = True,
-                     doping_points=(), harvest_every: int = 0, exp_all: bool = False, collect: bool = True):
-    """Unlimited-iteration full BP over a stream of ``frames_per_graph`` frames per graph with lane recycling
-    (``scldpc_bp_stream``).  Frame f of graph g is the channel realisation ``generate_erasures(..., first_frame=...)``
+                     doping_points=(), harvest_every: int = 0, exp_all: bool = False, collect: bool = True, max_it: int = 0):
+    """Full BP (unlimited, or at most ``max_it`` iterations per frame) over a stream of ``frames_per_graph`` frames per
+    graph with lane recycling (``scldpc_bp_stream``).  Frame f of graph g is the channel realisation ``generate_erasures(..., first_frame=...)``
     puts in lane f - first_frame; the graphs are the ones resident in ``fb`` (``fb.n_frames`` lanes are used)."""
     L = _lib.lib()
     G, B = fb.n_graphs, int(frames_per_graph)
@@ -297,7 +297,7 @@ def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, firs
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p).value
     flags = (F_TERMINATED if is_term else 0) | (F_EXP_ALL if exp_all else 0)
     cfg = _lib.StreamCfg(B, int(harvest_every), flags, len(hard), len(soft_p), ptr(eps_arr), ptr(a_h), ptr(a_sp), ptr(a_sc),
-                         int(seed), int(first_graph_id))
+                         int(seed), int(first_graph_id), max(0, int(max_it)))
     res = torch.zeros((5, G, B), dtype=torch.int32, device=fb.device)
     out = _lib.StreamOut(*[res[i].data_ptr() for i in range(5)])
     need = L.scldpc_bp_stream_workspace_bytes(ctypes.byref(fb.dims))

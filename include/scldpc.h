@@ -145,6 +145,8 @@ typedef struct {
     const double *eps_host;          /* [G] erasure probability of each graph's channel                        */
     const int32_t *doped_pos_host, *soft_pos_host, *soft_count_host;   /* doping as in scldpc_channel_generate  */
     uint64_t seed, first_graph_id;
+    int32_t max_it;                  /* iteration cap per frame, do {} while (iter < MaxNumIt) (BP_FULL.c:1066); <= 0: none.
+                                        Needs the node-state sweeps (the default)                              */
 } scldpc_stream_cfg_t;
 typedef struct {
     int32_t *iters_dev, *residual_dev, *blocks_err_dev, *erasures_exp_dev, *blocks_err_exp_dev;

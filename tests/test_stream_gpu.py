@@ -16,13 +16,13 @@ def stream_kernels(request, monkeypatch):
     return request.param
 
 
-def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
+def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=(), max_it=0):
     """frames 0..B-1 decoded 128 at a time with the synchronous message-passing decoder on the same graphs"""
     import os
     old = os.environ.get("SCLDPC_FULL_NODE")
     os.environ["SCLDPC_FULL_NODE"] = "0"
     try:
-        return _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping)
+        return _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping, max_it)
     finally:
         if old is None:
             del os.environ["SCLDPC_FULL_NODE"]
@@ -30,7 +30,7 @@ def sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
             os.environ["SCLDPC_FULL_NODE"] = old
 
 
-def _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
+def _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=(), max_it=0):
     G = fb_graphs.n_graphs
     out = {k: np.zeros((G, B), np.int32) for k in KEYS}
     for f0 in range(0, B, 128):
@@ -38,7 +38,7 @@ def _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=()):
         fb = eng.FrameBatch(ens, G, k, 2)
         fb.vn_cn.copy_(fb_graphs.vn_cn); fb._build_tables()
         fb.generate_erasures(eps, seed, first_graph_id=3, doping_points=doping, first_frame=f0)
-        r = eng.decode_bp_full(fb, 0, is_term)
+        r = eng.decode_bp_full(fb, max_it, is_term)
         for key in KEYS:
             out[key][:, f0:f0 + k] = getattr(r, key)
     return out
@@ -82,6 +82,26 @@ def test_stream_every_instantiated_degree(dv, dc, L, M):
         s = eng.decode_bp_stream(fbg, 500, eps, 21, first_graph_id=3, is_term=is_term)
         for key in KEYS:
             assert (getattr(s, key) == ref[key]).all(), (is_term, key)
+
+
+@pytest.mark.parametrize("cap", [1, 2, 9, 40])
+def test_capped_stream_equals_capped_synchronous_batches(cap, stream_kernels):
+    """lane recycling with an iteration cap per frame (do {} while (iter < MaxNumIt), BP_FULL.c:1066): frames that hit the
+    cap keep the erased set of that iteration while they wait for the harvest"""
+    ens = eng.Ensemble(4, 8, 12, 48)
+    fbg = eng.FrameBatch(ens, 2, 192).generate_graphs(17, first_graph_id=3)
+    eps = [0.46, 0.51]
+    if stream_kernels == "messages":
+        with pytest.raises(eng.ScldpcError):
+            eng.decode_bp_stream(fbg, 64, eps, 5, first_graph_id=3, max_it=cap)
+        return
+    for is_term in (True, False):
+        ref = sync_reference(fbg, ens, 600, eps, 5, is_term, max_it=cap)
+        for H in (0, 1, 5):
+            s = eng.decode_bp_stream(fbg, 600, eps, 5, first_graph_id=3, is_term=is_term, harvest_every=H, max_it=cap)
+            for key in KEYS:
+                assert (getattr(s, key) == ref[key]).all(), (is_term, H, key)
+        assert ref["iters"].max() <= cap
 
 
 def test_stream_full_size_sample():
