@@ -89,6 +89,8 @@ def _parser(prog):
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--frames-per-graph", type=int, default=128)
     ap.add_argument("--graphs-per-batch", type=int, default=4)
+    ap.add_argument("--stream", choices=["auto", "on", "off"], default="auto",
+                    help="bp_lim_iter: decode each graph's frames as a stream with lane recycling (auto: from 1024 frames per graph)")
     ap.add_argument("--compat-argv", action="store_true", help="read doped positions from argv[4] on like the reference")
     ap.add_argument("--outdir", default=".")
     return ap
@@ -119,6 +121,7 @@ def run(prog: str, argv=None) -> int:
     rank, world = D.init_from_env()
     graph_id = 0
     sw = prog == "sw_lim_iter"
+    use_stream = prog == "bp_lim_iter" and (a.stream == "on" or (a.stream == "auto" and fpg >= 1024))
     for sim in range(a.points):
         eps = a.eps_ini - sim * a.eps_delta                            # inizio_sim, BP_FULL.c:300
         c = new_counters()
@@ -136,6 +139,24 @@ def run(prog: str, argv=None) -> int:
         while f < a.max_frames and not stop:
             gid = graph_id + (rnd * world + rank) * G
             rnd += 1
+            if use_stream:
+                # same graphs and channel realisations as below (frame f of graph g is the same Philox draw), decoded on at
+                # most 1024 lanes per graph: a lane whose frame has stopped or hit the cap takes the graph's next frame
+                lanes = min(fpg, 1024)
+                fb = engine.FrameBatch(ens, G, lanes, engine.words_for(lanes))
+                fb.generate_graphs(seed, first_graph_id=gid)
+                r = engine.decode_bp_stream(fb, fpg, eps, seed + 1, first_graph_id=gid, is_term=True, doping_points=doped, max_it=max_it)
+                rec = np.stack([r.residual, r.blocks_err, r.erasures_exp, r.blocks_err_exp, np.zeros_like(r.residual), r.iters],
+                               axis=-1).astype(np.int64)
+                rec = D.allgather_rows(rec).reshape(-1, 6)
+                for k in range(len(rec)):
+                    if f >= a.max_frames or stop:
+                        break
+                    account(c, rec[k, 0], rec[k, 1], rec[k, 2], rec[k, 3], rec[k, 4])
+                    f += 1
+                    if c["frame_err"] >= a.min_frame_err:
+                        stop = True
+                continue
             fb = engine.FrameBatch(ens, G, fpg, nw)
             fb.generate_graphs(seed, first_graph_id=gid)
             fb.generate_erasures(eps, seed + 1, first_graph_id=gid, doping_points=doped)

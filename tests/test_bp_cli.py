@@ -49,3 +49,21 @@ def test_cli_end_to_end(tmp_path):
     first = [ln.split("\t") for ln in frames[0].split("\n")]
     assert [int(r[0]) for r in first] == list(range(len(first))) and all(len(r) == 4 for r in first)
     assert int(first[0][2]) > 0 and int(first[-1][3]) <= 10
+
+
+@pytest.mark.gpu
+def test_bp_lim_iter_stream_path_writes_the_same_file(tmp_path):
+    """bp_lim_iter decodes each graph's frames as a capped stream with lane recycling when asked to (and by default from
+    1024 frames per graph): same Philox realisations, so the result file is byte-identical to the synchronous path"""
+    files = {}
+    for mode in ("off", "on"):
+        out = tmp_path / mode
+        out.mkdir()
+        bp_cli.run("bp_lim_iter", ["3", "0", "1", "12", "4", "--L", "12", "--M", "24", "--outdir", str(out), "--seed", "9", "--points", "2",
+                                   "--eps-ini", "0.48", "--eps-delta", "0.03", "--frames-per-graph", "300", "--graphs-per-batch", "2",
+                                   "--min-frame-err", "60", "--max-frames", "1500", "--stream", mode])
+        (name,) = os.listdir(out)
+        files[mode] = (name, open(out / name).read())
+    assert files["on"] == files["off"]
+    rows = files["on"][1].splitlines()
+    assert len(rows) == 3 and float(rows[1].split()[2]) > 0          # header + 2 points, some frame errors at eps = 0.48
