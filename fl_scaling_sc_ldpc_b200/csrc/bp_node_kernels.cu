@@ -126,7 +126,9 @@ template <bool ARM, bool CAPPED>
 __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
 {
     pdl_wait_then_release();
-    const int g = blockIdx.y;
+    // the CN sweep walks graphs and rows upwards, this pass downwards (vn_reverse): the CN sweep then starts on the rows
+    // this pass touched last -- its first gathers are L2 hits
+    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
@@ -151,14 +153,16 @@ __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
             unsigned char ds[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int idx = base + u * (int)blockDim.x;
+                const int lin = base + u * (int)blockDim.x;
+                const int idx = p.vn_reverse ? ((p.n - 1 - (lin >> p.chunk_shift)) << p.chunk_shift) + k : lin;
                 xs[u] = zero128(); ds[u] = 0;
-                if (idx < items) { xs[u] = ld_cg128(xb + idx); ds[u] = dirty[idx]; }   // the CN sweep wrote xb with atomics (L2)
+                if (lin < items) { xs[u] = ld_cg128(xb + idx); ds[u] = dirty[idx]; }   // the CN sweep wrote xb with atomics (L2)
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int idx = base + u * (int)blockDim.x;
-                if (idx >= items) break;
+                const int lin = base + u * (int)blockDim.x;
+                if (lin >= items) break;
+                const int idx = p.vn_reverse ? ((p.n - 1 - (lin >> p.chunk_shift)) << p.chunk_shift) + k : lin;
                 u128 xn = xs[u];
                 const bool d = ds[u] != 0;
                 bool wr_x = d, wr_b = false;
