@@ -4,26 +4,32 @@
     python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...   the reference's CPU decoder on the host cores
 
-A *step* decodes 4 graph realisations (one per eps of the 0.46..0.49 sweep of BASELINE config 2) x B frames each
-(default B = 16384, 1024 bit-sliced lanes per graph), full BP with unlimited iterations until every frame has stalled
-or finished.  Default mode "stream": a lane whose frame has stopped is re-armed with the graph's next channel
-realisation (scldpc_bp_stream); mode "batch": B = lanes, every lane decodes one frame (scldpc_bp_full).  Throughput counts USEFUL
-work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same formula as for the CPU
-(SURVEY.md section 8d); iterations a finished frame rides along for do not count.
+Headline (BASELINE config 2).  A *step* draws 4 NEW graph realisations (one per eps of the 0.46..0.49 sweep) on the device
+-- scldpc_graph_generate + scldpc_graph_build_tables run INSIDE the timed region -- and decodes --frames-per-graph
+(default 16384) fresh channel realisations on each with full BP, unlimited iterations, until every frame has stalled or
+finished.  1024 bit-sliced lanes per graph; a lane whose frame has stopped is re-armed with the graph's next channel
+realisation (scldpc_bp_stream), so a graph is reused for frames_per_graph frames (the reference draws a graph per frame,
+BP_FULL.c:2122; the reuse is stated in `config` and the workload "bp_full_fpg1024" reports the same step at 1024 frames
+per graph).  Graph ids are global and never repeat: every step, warm-up included, decodes new realisations.
+Throughput counts USEFUL work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same
+formula as for the CPU; iterations a finished frame rides along for do not count.
 
-value : batches resident in HBM, decode + per-frame counters on the device.
-e2e   : the same step through the host-buffer C-ABI call scldpc_decode_host: graph tables and bit-sliced channel
-        words start in pinned HOST memory, results end in host memory; H2D / D2H inside the timed region.
-roofline : one flooding iteration of the stream decoder (node-state sweeps: ns_cn_kernel + ns_x_kernel), algorithmic bytes
-        B_alg = (4E+n)/8 per useful frame-iteration (the message formulation's figure) over the CUDA-event time
-        of sampled launches inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth; the DRAM bytes ncu
-        measured and the node-state minimum are reported beside it.  SCLDPC_STREAM_NODE=0 / --mode batch run the
-        message-passing sweeps, for which the VN sweep is reported as before.
+value    : the step above, everything on the device.
+e2e      : the same step through the host-buffer C-ABI call scldpc_stream_host: graph tables start in pinned HOST memory
+           (a different set every step), per-frame results end in host memory; H2D / D2H inside the timed region.
+roofline : one flooding iteration of the stream decoder (ns_iter_kernel, bp_node_kernels.cu): algorithmic bytes
+           B_alg = (4E+n)/8 per useful frame-iteration (the message formulation's figure) over the CUDA-event
+           time of sampled launches inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth; ncu's DRAM
+           bytes and the node-state minimum are reported beside it.
+workloads: (N = 1 only) the other BASELINE configs, each timed on the device with its own roofline and CPU baseline:
+           turnover at 1024 frames per graph, message-passing sweeps, peeling trajectories (config 1), capped BP with
+           trajectory rows (config 3), sliding window L=100 (config 4).
 cpu_baseline : the unmodified reference decodeBP (oracle/_ref, compiled from /root/reference) on the host cores.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -37,28 +43,30 @@ sys.path.insert(0, ROOT)
 DV, DC, L, M = 4, 8, 50, 10000
 EPS_SWEEP = [0.46, 0.47, 0.48, 0.49]
 N_WORDS = 16
-FRAMES_PER_GRAPH = 64 * N_WORDS
 E_EDGES = L * M * DV
 N_VNS = L * M
 N_CNS = (L + DV - 1) * (M * DV // DC)
-WORKLOAD = ("full BP unlimited iterations, (4,8) SC-LDPC terminated L=50 M=10000, BEC eps sweep "
-            "{0.46,0.47,0.48,0.49}: 4 graphs x B frames per step")
+B_ALG = (4 * E_EDGES + N_VNS) / 8.0          # bytes per frame-iteration, message formulation
 FRAMES_PER_STREAM = 16384
-HARVEST_EVERY = 0        # 0: the library adapts the period to the iterations per frame it observes
 CAP_LO = 2   # reference arm: iterations of the shorter of the two capped runs
 METRIC = "edge-updates/s (frames/s alongside), (4,8) SC-LDPC L=50 M=10000 BEC BP"
 
 
+def workload_name(fpg: int) -> str:
+    return (f"full BP unlimited iterations, (4,8) SC-LDPC terminated L=50 M=10000, BEC eps sweep {{0.46,0.47,0.48,0.49}}: "
+            f"4 new graphs x {fpg} frames per graph per step")
+
+
 # ------------------------------------------------------------------------------------------------------------------
-# reference arm: the reference's own decodeBP on the host cores
+# reference arm: the reference's own decoders on the host cores
 # ------------------------------------------------------------------------------------------------------------------
 def _ref_worker(args):
     """One frame on one core: generate_code + channel_doped, then decodeBP twice on the same frame, capped at CAP_LO
     and at CAP_LO+cap flooding iterations.  The difference of the two times is the cost of `cap` iterations of the
     reference's sweeps over the full-size frame; the common part (message initialisation) is subtracted out.  The
     post-decoding expurgation scan -- quadratic in the erasures a capped run leaves behind, negligible for a
-    converged frame -- is skipped by passing decodeBP's L argument (used only as that scan's range) as 0.  Uses BP_TRAJ.c's decodeBP (same loops as BP_FULL.c's plus one fprintf per iteration) so that
-    the number of executed iterations is known."""
+    converged frame -- is skipped by passing decodeBP's L argument (used only as that scan's range) as 0.  Uses BP_TRAJ.c's
+    decodeBP (same loops as BP_FULL.c's plus one fprintf per iteration) so that the number of executed iterations is known."""
     seed, eps, cap = args
     from oracle import ref_driver as rd
     r = rd.get("traj", DV, DC, L, M * DV // DC)
@@ -89,6 +97,63 @@ def _port_worker(args):
     return b["iters"] - a["iters"], (t2 - t1) - (t1 - t0)
 
 
+def _ref_window_worker(args):
+    """decodeBP_SW of the unmodified BP_SW.c (square window) on one full-size frame of config 4; eps low enough for the
+    window decoder to succeed, so the expurgation scan has nothing to do.  Returns (edge updates, seconds)."""
+    seed, eps, W, cap, init = args
+    from oracle import ref_driver as rd
+    Lw = 100
+    r = rd.get("sw", DV, DC, Lw, M * DV // DC)
+    r.srandom(seed)
+    r.reset_perm()
+    r.generate_code()
+    r.channel_doped(eps)
+    t0 = time.perf_counter()
+    r.decode_bp_sw(W, cap, init)
+    dt = time.perf_counter() - t0
+    # executed iterations are not returned by the reference: count the work of a run that uses every allowed iteration,
+    # which is an UPPER bound of what it executed (favours the CPU)
+    its = init + (Lw - 1) * cap
+    return its * 2 * W * M * DV, dt
+
+
+def _peel_port_worker(args):
+    """config 1 on one core: the oracle port of simulate_peeling_decoder_ldpc's frame loop (PD.py:740-785)"""
+    seed, Mp, nfr = args
+    import numpy as np
+    import oracle
+    l, r, Lp, e = 4, 8, 50, 0.48
+    cns = Mp * l // r
+    total_size = cns * Lp
+    steps = int(Mp * Lp * (e + 0.1))
+    oracle.srandom(seed)
+    g, _ = oracle.generate_code(Lp, Mp, cns, l, r)
+    rng = np.random.default_rng(seed)
+    t = 0.0
+    for _ in range(nfr):
+        er = (rng.random(Lp * Mp) <= e).astype(np.uint8)
+        picks = rng.integers(0, 2 ** 32, steps, dtype=np.uint32)
+        t0 = time.perf_counter()
+        oracle.peel_trajectory(g.vn_cn, er, total_size, g.nk, steps, picks)
+        t += time.perf_counter() - t0
+    return nfr * steps, t
+
+
+def _preload_reference_libraries():
+    """dlopen the compiled reference in THIS process before the workers fork, so the process that prints the line is the
+    one that has oracle/_ref/*.so mapped (the driver records which shared objects a bench process loaded)."""
+    from oracle import ref_driver as rd
+    loaded = []
+    for variant, Lr in (("traj", L), ("sw", 100)):
+        if rd.available(variant, DV, DC, Lr, M * DV // DC):
+            try:
+                rd.get(variant, DV, DC, Lr, M * DV // DC)
+                loaded.append(os.path.basename(rd.build_ref.so_name(variant, DV, DC, Lr, M * DV // DC)))
+            except Exception:
+                pass
+    return loaded
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -96,11 +161,13 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle import ref_driver as rd
     cores = os.cpu_count() or 1
+    loaded = _preload_reference_libraries()
     have_ref = rd.available("traj", DV, DC, L, M * DV // DC)
     worker, kind = (_ref_worker, "reference") if have_ref else (_port_worker, "port")
     cap = args.sample_iters
     ctx = mp.get_context("fork")
     per_step = []
+    side = {}
     with ctx.Pool(cores) as pool:
         for s in range(args.warmup + args.steps):
             jobs = [(1000003 * (s + 1) + i, EPS_SWEEP[i % len(EPS_SWEEP)], cap) for i in range(cores)]
@@ -110,6 +177,23 @@ def run_reference(args):
             decode_wall = max(dt for _, dt in res)
             if s >= args.warmup:
                 per_step.append((sum(it for it, _ in res), decode_wall, wall))
+        if args.side_baselines:
+            # bounded samples for the side workloads of the default run (reported inside their workload entries)
+            if rd.available("sw", DV, DC, 100, M * DV // DC):
+                res = pool.map(_ref_window_worker, [(77 + i, 0.40, 5, 8, 60) for i in range(cores)])
+                side["window_W5"] = {"value": sum(w for w, _ in res) / max(dt for _, dt in res), "unit": "edge-updates/s (upper bound)",
+                                     "cores": cores, "kind": "reference",
+                                     "sample": f"{cores} processes x 1 frame, unmodified decodeBP_SW (BP_SW.c:628), L=100 M=10000 W=5, 8 iterations "
+                                               "per window / 60 for the first, eps=0.40; work counted as if every allowed iteration ran",
+                                     "frames_per_s": cores / max(dt for _, dt in res)}
+            for Mp, nfr in ((1000, 8), (10000, 1)):
+                res = pool.map(_peel_port_worker, [(5 + i, Mp, nfr) for i in range(cores)])
+                wall = max(dt for _, dt in res)
+                side[f"peeling_M{Mp}"] = {"value": sum(s_ for s_, _ in res) / wall, "unit": "peel-steps/s", "cores": cores, "kind": "port",
+                                          "frames_per_s": cores * nfr / wall,
+                                          "sample": f"{cores} processes x {nfr} frame(s), oracle port (C) of simulate_peeling_decoder_ldpc's frame loop "
+                                                    f"(PD.py:740-785), L=50 M={Mp} eps=0.48 non-terminated; the reference itself is Python: "
+                                                    "1.37 s/frame at M=1000 on one core (SURVEY section 6), ~58-72 s/frame at M=10000 (NB:705, NB:825)"}
     iters = sum(p[0] for p in per_step)
     t = sum(p[1] for p in per_step)
     eu = iters * 2.0 * E_EDGES / t
@@ -121,11 +205,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": eu, "unit": "edge-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, len(per_step)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (0/1 messages)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "frame_iterations_per_s": iters / t,
+        "data": "synthetic", "config": {"workload": workload_name(args.frames_per_graph)},
+        "frame_iterations_per_s": iters / t, "frames_per_s_at_348_iterations": iters / t / 348.0,
+        "reference_libraries_loaded": loaded,
         "cpu_baseline": {"value": eu, "unit": "edge-updates/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": eu, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if side:
+        line["side_baselines"] = side
     print(json.dumps(line))
     return 0
 
@@ -181,6 +268,234 @@ class ClockSampler:
         return out
 
 
+def _peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pk = {}
+    if "hbm_gbs" in pk:
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def _traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+class SweepProfile:
+    """CUDA-event samples of the sweeps of every `every`-th iteration (scldpc_profile_begin / _end)."""
+
+    def __init__(self, lib, check, every=13, cap=16384):
+        self.lib, self.check, self.cap = lib, check, cap
+        check(lib.scldpc_profile_begin(every, cap))
+
+    def end(self):
+        import numpy as np
+        ns = ctypes.c_int(0)
+        it = (ctypes.c_int * self.cap)()
+        a = (ctypes.c_float * self.cap)()
+        b = (ctypes.c_float * self.cap)()
+        self.check(self.lib.scldpc_profile_end(ctypes.byref(ns), it, a, b, self.cap))
+        n = ns.value
+        return np.asarray(a[:n], dtype=np.float64), np.asarray(b[:n], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# side workloads (N = 1): the other BASELINE configs, device-timed
+# ------------------------------------------------------------------------------------------------------------------
+def side_workloads(args, dev, side_cpu):
+    import numpy as np
+    import torch
+
+    import fl_scaling_sc_ldpc_b200 as eng
+    from fl_scaling_sc_ldpc_b200 import _lib
+    from fl_scaling_sc_ldpc_b200 import peeling_decoding as pdx
+
+    lib = _lib.lib()
+    peak, peak_src = _peaks()
+    tj = _traffic()
+    out = {}
+    want = set(args.workloads.split(",")) if args.workloads not in ("all", "") else None
+
+    def timed(fn, steps, warm=1):
+        for i in range(warm):
+            fn(-1 - i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lib.scldpc_launch_count(1)
+        e0.record()
+        acc = [fn(i) for i in range(steps)]
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3, acc, int(lib.scldpc_launch_count(1))
+
+    ens = eng.Ensemble(DV, DC, L, M)
+    eps4 = EPS_SWEEP
+
+    # ---- turnover: a new graph for every 1024 frames, generation inside the timed region
+    if want is None or "bp_full_fpg1024" in want:
+        cfgs = {}
+        for nw, G in ((16, 4), (4, 16)):
+            lanes = 64 * nw
+            fb = eng.FrameBatch(ens, G, lanes, nw, device=dev)
+            eps = [e for e in eps4 for _ in range(G // 4)]
+            tg = []
+
+            def step(i, fb=fb, eps=eps, G=G, tg=tg):
+                gid = (1 << 20) + (i + 8) * G
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                fb.generate_graphs(seed=args.seed, first_graph_id=gid)
+                g1.record()
+                res, _ = eng.decode_bp_stream(fb, 1024, eps, args.seed + 1, first_graph_id=gid, collect=False)
+                tg.append((g0, g1))
+                return res
+            steps = 8 if nw == 16 else 2
+            dt, acc, launches = timed(step, steps)
+            its = sum(int(r[0].sum().item()) for r in acc)
+            nfail = sum(int((r[1] > 0).sum().item()) for r in acc)
+            frames = steps * G * 1024
+            g_ms = sum(a.elapsed_time(b) for a, b in tg[1:]) / (steps * G)      # tg[0] is the warm-up step
+            cfgs[f"n_words={nw}"] = {"value": its * 2.0 * E_EDGES / dt, "unit": "edge-updates/s", "frames_per_s": frames / dt,
+                                     "graphs_per_step": G, "lanes_per_graph": lanes, "frames_per_graph": 1024, "steps": steps,
+                                     "ms_per_step": 1e3 * dt / steps, "ms_per_generated_graph": g_ms,
+                                     "graph_generation_share": g_ms * G * steps / (1e3 * dt),
+                                     "frame_error_rate": nfail / frames, "gpu_launches": launches}
+            del fb, acc
+            torch.cuda.empty_cache()
+        best = max(cfgs, key=lambda k: cfgs[k]["value"])
+        out["bp_full_fpg1024"] = dict(cfgs[best], layout=best, layouts=cfgs,
+                                      note="scldpc_graph_generate + scldpc_graph_build_tables + fresh frame ids inside the timed region; every "
+                                           "graph decodes exactly 1024 frames (the reference draws a graph per frame, BP_FULL.c:2117-2143); "
+                                           "n_words=16: one frame per lane, n_words=4: 256 lanes per graph recycled four times")
+
+    # ---- message-passing sweeps (the implementation of record): the formulation that really moves B_alg through HBM
+    if want is None or "bp_full_messages" in want:
+        fb = eng.FrameBatch(ens, 4, 1024, 16, device=dev)
+        fb.generate_graphs(seed=args.seed, first_graph_id=3 << 20)
+        Bm = 4096
+
+        def step(i):
+            res, launched = eng.decode_bp_stream(fb, Bm, eps4, args.seed + 1, first_graph_id=(3 << 20) + 4 * (i + 2), collect=False, messages=True)
+            return int(res[0].sum().item()), int(launched)
+        step(-1)
+        prof = SweepProfile(lib, _lib.check)
+        dt, acc, launches = timed(step, 2, warm=0)
+        cn_ms, vn_ms = prof.end()
+        its = sum(a for a, _ in acc)
+        fi_per_launch = its / max(1, sum(b for _, b in acc))
+        cn_b, vn_b = fi_per_launch * 2 * E_EDGES / 8.0, fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
+        ach = (cn_b + vn_b) / ((cn_ms.mean() + vn_ms.mean()) * 1e-3) / 1e9
+        out["bp_full_messages"] = {
+            "value": its * 2.0 * E_EDGES / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * Bm / dt, "frames_per_graph": Bm,
+            "ms_per_step": 1e3 * dt / 2, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "bp_cn_wave_kernel<8,false> + bp_vn_stream_kernel<4> (one flooding iteration)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                         "traffic": (tj.get("vn_sweep_dram_bytes_per_launch", 0) + tj.get("cn_sweep_dram_bytes_per_launch", 0)) or None,
+                         "avg_launch_ms": [float(cn_ms.mean()), float(vn_ms.mean())], "launches_sampled": int(len(cn_ms)),
+                         "frame_iterations_per_launch": fi_per_launch,
+                         "cn_sweep": {"achieved": cn_b / (cn_ms.mean() * 1e-3) / 1e9, "frac": cn_b / (cn_ms.mean() * 1e-3) / 1e9 / peak},
+                         "vn_sweep": {"achieved": vn_b / (vn_ms.mean() * 1e-3) / 1e9, "frac": vn_b / (vn_ms.mean() * 1e-3) / 1e9 / peak},
+                         "algorithmic_bytes": "(4E+n)/8 B per useful frame-iteration: 2E/8 CN sweep + (2E+n)/8 VN sweep"}}
+        del fb
+        torch.cuda.empty_cache()
+
+    # ---- config 3: iteration-limited BP with per-iteration trajectory rows
+    if want is None or "bp_capped_175_traj" in want:
+        cap = 175
+        fb = eng.FrameBatch(ens, 4, 1024, 16, device=dev)
+        fb.generate_graphs(seed=args.seed, first_graph_id=5 << 20)
+
+        def step(i):
+            fb.generate_erasures(eps4, args.seed + 1, first_graph_id=(5 << 20) + 4 * (i + 2))
+            res, erased, rows, launched = eng.decode_bp_full(fb, cap, True, trajectory=True, max_rows=cap, collect=False)
+            return int(res[0].sum().item()), int(launched), int(rows[:, :, :, 1].sum().item())
+        step(-1)
+        prof = SweepProfile(lib, _lib.check, every=7)
+        dt, acc, launches = timed(step, 2, warm=0)
+        cn_ms, vn_ms = prof.end()
+        its = sum(a[0] for a in acc)
+        fi_per_launch = its / max(1, sum(a[1] for a in acc))
+        ach = fi_per_launch * B_ALG / ((cn_ms.mean() + vn_ms.mean()) * 1e-3) / 1e9
+        out["bp_capped_175_traj"] = {
+            "value": its * 2.0 * E_EDGES / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
+            "cap": cap, "trajectory_rows_per_step": 4 * 1024 * cap, "gpu_launches": launches,
+            "note": "channel generation, decode with (deg_1_iter, dVNs, first erased position) rows for every iteration, 4 graphs x 1024 frames",
+            "roofline": {"bound": "hbm", "kernel": "bp_cn_wave_kernel<8,true> + bp_vn_wave_kernel<4,true> (one flooding iteration, trajectory counters)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                         "avg_launch_ms": [float(cn_ms.mean()), float(vn_ms.mean())], "launches_sampled": int(len(cn_ms)),
+                         "frame_iterations_per_launch": fi_per_launch, "algorithmic_bytes": "(4E+n)/8 B per useful frame-iteration"}}
+        del fb
+        torch.cuda.empty_cache()
+
+    # ---- config 4: sliding window, L = 100, non-terminated (derived mode)
+    if want is None or "window_L100" in want:
+        ensw = eng.Ensemble(DV, DC, 100, M)
+        fb = eng.FrameBatch(ensw, 4, 1024, 16, device=dev)
+        fb.generate_graphs(seed=args.seed, first_graph_id=7 << 20)
+        wl = {}
+        for W, e in ((3, 0.36), (5, 0.40), (10, 0.45)):
+            def step(i, W=W, e=e):
+                fb.generate_erasures(e, args.seed + 1, first_graph_id=(7 << 20) + 4 * (i + 2))
+                res, erased, rows, _ = eng.decode_bp_window(fb, W, 8, 60, square=True, is_term=False, collect=False)
+                return res
+            step(-1)
+            prof = SweepProfile(lib, _lib.check, every=11)
+            dt, acc, launches = timed(step, 2, warm=0)
+            cn_ms, vn_ms = prof.end()
+            # useful work: the per-lane edge-update counters of a collecting call on the last step's realisations
+            r = eng.decode_bp_window(fb, W, 8, 60, square=True, is_term=False)
+            work = 2 * r.edge_updates
+            ach = work * (B_ALG / (2 * E_EDGES)) / dt / 1e9
+            wl[f"W={W}"] = {"value": work / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
+                            "eps": e, "frame_error_rate": float((r.residual > 0).mean()), "gpu_launches": launches,
+                            "roofline": {"bound": "hbm", "kernel": "bpw_cn_node_kernel<4,8> + bpw_vn_node_kernel (window iterations)",
+                                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                                         "traffic": (tj.get("window_node", {}) or {}).get(f"W{W}_dram_bytes_per_launch"),
+                                         "avg_launch_ms": [float(cn_ms.mean()), float(vn_ms.mean())] if len(cn_ms) else None,
+                                         "launches_sampled": int(len(cn_ms)),
+                                         "algorithmic_bytes": "0.2656 B per useful edge update (= (4E+n)/8 per frame-iteration of the window's "
+                                                              "edges, message formulation); the node-state sweeps move less, so frac can exceed 1"}}
+        out["window_L100"] = {"config": "(4,8) SC-LDPC non-terminated (derived mode) L=100 M=10000, square window, 8 iterations per window, "
+                                        "60 for the first; 4 graphs x 1024 frames per step, channel generation inside the timed region",
+                              "windows": wl, "cpu_baseline": (side_cpu or {}).get("window_W5")}
+        del fb
+        torch.cuda.empty_cache()
+
+    # ---- config 1: peeling trajectories
+    if want is None or "peeling" in want:
+        for Mp, G, F in ((1000, 8, 1024), (10000, 2, 256)):
+            l, r, Lp, e = 4, 8, 50, 0.48
+            ensp = eng.Ensemble(l, r, Lp, Mp)
+            cns, num_positions, total_size, steps = pdx._peel_geometry(e, l, r, Lp, Mp, False)
+            fb = eng.FrameBatch(ensp, G, F, device=dev)
+
+            def step(i, fb=fb, ensp=ensp, total_size=total_size, steps=steps, G=G, F=F):
+                gid = (9 << 20) + (i + 2) * G
+                fb.generate_graphs(args.seed, first_graph_id=gid)
+                fb.generate_erasures(e, args.seed + 1, first_graph_id=gid)
+                r1, rec, ner = pdx.peel_batch(ensp, fb, total_size, steps, args.seed + 2, gid * F)
+                return int(rec.sum().item())
+            dt, acc, launches = timed(step, 2)
+            frames = 2 * G * F
+            psteps = frames * steps
+            out[f"peeling_M{Mp}"] = {"value": psteps / dt, "unit": "peel-steps/s", "frames_per_s": frames / dt, "ms_per_step": 1e3 * dt / 2,
+                                     "config": f"peeling decoding trajectories, (4,8) SC-LDPC L=50 M={Mp} non-terminated eps=0.48, "
+                                               f"{G} new graphs x {F} frames per step, r1 int32[{steps + 1}] per frame materialised in HBM",
+                                     "recovered_vns_per_frame": sum(acc) / frames, "gpu_launches": launches,
+                                     "roofline": {"bound": "hbm", "kernel": "peel_trajectory_kernel (one warp per frame; latency-bound chain of dependent steps)",
+                                                  "achieved": psteps * 36.0 / dt / 1e9, "peak": peak, "unit": "GB/s", "frac": psteps * 36.0 / dt / 1e9 / peak,
+                                                  "peak_source": peak_src, "traffic": None,
+                                                  "algorithmic_bytes": "36 B per peel step (16 B adjacency + 4 x 4 B degree updates + 4 B r1), SURVEY 8d"},
+                                     "cpu_baseline": (side_cpu or {}).get(f"peeling_M{Mp}")}
+            del fb
+            torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -189,18 +504,21 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    cpu_baseline = None
+    cpu_baseline = side_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # timed before CUDA is initialised in this process (the workers fork)
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "0",
-                                "--sample-iters", str(args.sample_iters)], capture_output=True, text=True, timeout=900)
-            cpu_baseline = json.loads(p.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "0",
+                   "--sample-iters", str(args.sample_iters)]
+            if args.workloads != "none":
+                cmd.append("--side-baselines")
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+            ref_line = json.loads(p.stdout.strip().splitlines()[-1])
+            cpu_baseline = ref_line["cpu_baseline"]
+            side_cpu = ref_line.get("side_baselines")
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": "edge-updates/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"failed: {e!r}"}
-
-    import ctypes
 
     import numpy as np
     import torch
@@ -216,38 +534,39 @@ def run_ours(args):
     lib = _lib.lib()
     ens = eng.Ensemble(DV, DC, L, M)
     stream_mode = args.mode == "stream"
-    lanes = FRAMES_PER_GRAPH                                     # bit-sliced lanes per graph
+    lanes = 64 * N_WORDS                                         # bit-sliced lanes per graph
     B = args.frames_per_graph if stream_mode else lanes         # frames decoded per graph and step
     G = len(EPS_SWEEP) * args.graphs_per_eps
     eps = [e for e in EPS_SWEEP for _ in range(args.graphs_per_eps)]
     eps_arr = np.asarray(eps, np.float64)
+    messages = os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") == "0"
+    sflag = _lib.F_MESSAGES if messages else 0
 
-    # two resident batches, alternated, each an independent draw: graph ids are global, so the realisations (and
-    # therefore the results) do not depend on how many GPUs share the job
-    batches = []
-    for bidx in range(2):
-        gid0 = (rank * 2 + bidx) * G
-        fb = eng.FrameBatch(ens, G, lanes, N_WORDS, device=dev)
-        fb.generate_graphs(seed=args.seed, first_graph_id=gid0)
-        if not stream_mode:
-            fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid0)
-        fb.gid0 = gid0
-        batches.append(fb)
-    torch.cuda.synchronize()
+    # graph ids are global and never reused: step s of rank r decodes graphs [(s*world + r)*G, +G) -- warm-up steps first --
+    # so the realisations (and therefore the results) do not depend on how many GPUs share the job
+    def gid_of(step_index):
+        return (step_index * world + rank) * G
 
+    fb = eng.FrameBatch(ens, G, lanes, N_WORDS, device=dev)
     counters = torch.zeros(4, dtype=torch.int64, device=dev)   # frame-iterations, frames, frame errors, bit errors
+    iters_launched = [0]                                       # iterations launched by this rank in the timed region
+    graph_events = []
 
-    iters_launched = [0]                                       # sweep pairs launched by this rank in the timed region
-
-    def step(i, acc=True):
-        fb = batches[i % 2]
+    def step(s, acc=True):
+        gid = gid_of(s)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        fb.generate_graphs(seed=args.seed, first_graph_id=gid)         # scldpc_graph_generate + scldpc_graph_build_tables
+        g1.record()
         if stream_mode:
-            res, launched = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=fb.gid0, harvest_every=args.harvest_every, collect=False)
+            res, launched = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=gid, harvest_every=args.harvest_every, collect=False)
             it, resid = res[0].to(torch.int64), res[1].to(torch.int64)
         else:
+            fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid)
             res, erased, rows, launched = eng.decode_bp_full(fb, eng.UNLIMITED, True, collect=False)
             it, resid = res[0, :, :lanes].to(torch.int64), res[1, :, :lanes].to(torch.int64)
         if acc:
+            graph_events.append((g0, g1))
             iters_launched[0] += int(launched)
             counters.add_(torch.stack([it.sum(), torch.tensor(it.numel(), device=dev), (resid > 0).sum(), resid.sum()]))
 
@@ -260,30 +579,25 @@ def run_ours(args):
         step(i, acc=False)
     barrier()
 
-    # ---- timed region: K steps, device-resident inputs ---------------------------------------------------------
-    sample_every = 13       # co-prime with the harvest periods in use, so sampled launches are representative
-    _lib.check(lib.scldpc_profile_begin(sample_every, 16384))
+    # ---- timed region: K steps ------------------------------------------------------------------------------------
+    prof = SweepProfile(lib, _lib.check, every=13)       # co-prime with the harvest periods in use
     lib.scldpc_launch_count(1)
     clocks = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
     for i in range(args.steps):
-        step(i)
+        step(args.warmup + i)
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms_local = ev0.elapsed_time(ev1)
     launches = lib.scldpc_launch_count(1)
     clk = clocks.stop()
-    cap = 16384
-    ns = ctypes.c_int(0)
-    it_idx = (ctypes.c_int * cap)()
-    cn_ms = (ctypes.c_float * cap)()
-    vn_ms = (ctypes.c_float * cap)()
-    _lib.check(lib.scldpc_profile_end(ctypes.byref(ns), it_idx, cn_ms, vn_ms, cap))
+    cn_ms, vn_ms = prof.end()
+    graph_ms = sum(a.elapsed_time(b) for a, b in graph_events)
 
     local_frame_iters = int(counters[0].item())
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     tot = counters.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -293,116 +607,98 @@ def run_ours(args):
     value = frame_iters * 2.0 * E_EDGES / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
-    # algorithmic bytes per launch = useful frame-iterations of the timed region / sweeps launched x bytes per
-    # frame-iteration of that sweep; average launch duration from the CUDA-event samples (every 7th iteration)
     roof = kernels = None
-    if rank == 0 and ns.value > 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        n_s = ns.value
-        cn_avg = float(np.mean(cn_ms[:n_s])) * 1e-3
-        vn_avg = float(np.mean(vn_ms[:n_s])) * 1e-3
-        n_iter_launches = iters_launched[0] or n_s * sample_every  # iterations launched by this rank in the timed region
-        fi_per_launch = local_frame_iters / max(1, n_iter_launches)
-        cn_bytes = fi_per_launch * (2 * E_EDGES) / 8.0
-        vn_bytes = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
-        node_state = os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") != "0"
-        k_cn, k_x = ("ns_cn_kernel<4,8>", "ns_x_kernel") if stream_mode else ("bpw_cn_node_kernel<4,8>", "bpw_vn_node_kernel")
-        tj = {}
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            try:
-                tj = json.load(open(tpath))
-            except Exception:
-                tj = {}
-        if node_state:
-            # Node-state sweeps (bp_node_kernels.cu): the first timed kernel is the CN sweep (gathers E rows of x, scatters
-            # the resolutions), the second the sequential state pass.  SURVEY 8(d): the denominator of record stays the
-            # message formulation's B_alg = (4E+n)/8 B per frame-iteration; the DRAM bytes ncu measured and the
-            # node-state minimum (2n+nk)/8 are reported next to it, so a fraction above 1 is explained, not hidden.
-            it_bytes = fi_per_launch * (4 * E_EDGES + N_VNS) / 8.0
-            ach = it_bytes / (cn_avg + vn_avg) / 1e9
-            tn = tj.get("node_state", {}) if stream_mode else {}
+    if rank == 0 and len(cn_ms) > 0:
+        peak, peak_src = _peaks()
+        tj = _traffic()
+        n_s = len(cn_ms)
+        cn_avg, vn_avg = float(cn_ms.mean()) * 1e-3, float(vn_ms.mean()) * 1e-3
+        fi_per_launch = local_frame_iters / max(1, iters_launched[0])
+        pct = lambda a, q: float(np.percentile(a, q))
+        if not messages:
+            # Node-state sweeps.  SURVEY 8(d): the denominator of record stays the message formulation's B_alg = (4E+n)/8 B per
+            # frame-iteration; the DRAM bytes ncu measured and the node-state minimum (2n+nk)/8 are reported next to it, so a
+            # fraction above 1 is explained, not hidden.
+            if stream_mode:
+                kname, tn = "ns_iter_kernel<4,8,false>", tj.get("node_state_r2", {})
+                kwhat = "one flooding iteration = one launch: replay of the previous iteration's resolution lists + CN sweep + lane retirement"
+            else:
+                kname, tn = "bpw_cn_node_kernel<4,8> + bpw_vn_node_kernel", {}
+                kwhat = "one flooding iteration"
+            it_t = cn_avg + vn_avg
+            ach = fi_per_launch * B_ALG / it_t / 1e9
             traffic = tn.get("iteration_dram_bytes_per_launch")
-            roof = {"bound": "hbm", "kernel": k_cn + " + " + k_x + " (one flooding iteration)", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_note": tn.get("note"), "peak_source": peak_src, "launches_sampled": n_s,
-                    "avg_launch_ms": 1e3 * (cn_avg + vn_avg), "frame_iterations_per_launch": fi_per_launch,
+            roof = {"bound": "hbm", "kernel": kname, "kernel_does": kwhat, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "traffic_note": tn.get("note"), "peak_source": peak_src, "launches_sampled": n_s,
+                    "avg_launch_ms": 1e3 * it_t, "p10_p50_p90_ms": [pct(cn_ms + vn_ms, 10), pct(cn_ms + vn_ms, 50), pct(cn_ms + vn_ms, 90)],
+                    "frame_iterations_per_launch": fi_per_launch,
                     "algorithmic_bytes": "(4E+n)/8 B = 1.0625 MB per useful frame-iteration (message formulation, SURVEY 8d: the denominator of record)",
                     "node_state_min_bytes_per_launch": fi_per_launch * (2 * N_VNS + N_CNS) / 8.0,
-                    "explanation": "the node-state sweeps keep 1 bit per VN and frame instead of 2 bits per edge, and their gathers are served "
+                    "dram_frac_of_peak_one_graph": tn.get("dram_frac_of_peak"),
+                    "explanation": "the node-state sweep keeps 1 bit per VN and frame instead of 2 bits per edge, and its gathers are served "
                                    "by L2 (a band of dv positions); HBM traffic per iteration is a fraction of B_alg, so frac > 1 is expected. "
-                                   "The kernels are bound by L2->SM sector bandwidth: see l2 below",
-                    "l2": {"bytes_per_launch": tn.get("cn_l2_read_bytes_per_launch"), "note": tn.get("l2_note")}}
-            pct = lambda a, q: float(np.percentile(np.asarray(a[:n_s], dtype=np.float64), q))
-            kernels = {k_cn: {"avg_launch_ms": 1e3 * cn_avg, "p10_p50_p90_ms": [pct(cn_ms, 10), pct(cn_ms, 50), pct(cn_ms, 90)],
-                                             "share_of_iteration": cn_avg / (cn_avg + vn_avg),
-                                             "dram_bytes_per_launch": tn.get("cn_dram_bytes_per_launch")},
-                       k_x: {"avg_launch_ms": 1e3 * vn_avg, "p10_p50_p90_ms": [pct(vn_ms, 10), pct(vn_ms, 50), pct(vn_ms, 90)],
-                                       "share_of_iteration": vn_avg / (cn_avg + vn_avg),
-                                       "dram_bytes_per_launch": tn.get("x_dram_bytes_per_launch")}}
+                                   "The kernel is bound by L2 latency and instruction issue (profiles/README.md)",
+                    "l2": {"bytes_per_launch": tn.get("l2_read_bytes_per_launch"), "note": tn.get("l2_note")}}
+            kernels = {kname: {"avg_launch_ms": 1e3 * it_t, "share_of_iteration": 1.0 if stream_mode else None,
+                               "dram_bytes_per_launch": traffic}}
         else:
-            traffic = tj.get("vn_sweep_dram_bytes_per_launch")
-            traffic_note = None
-            if tj:
-                traffic_note = ("ncu --set full capture of one launch with %d graph(s) decoding (%s); the average launch of "
-                                "the timed region carries %.0f active frames" % (tj.get("graphs_decoding_in_captured_launch", 1),
-                                                                               tj.get("algorithmic_bytes_same_launch", ""), fi_per_launch))
-            vn_name = "bp_vn_stream_kernel<4>" if stream_mode else "bp_vn_wave_kernel<4,false>"
-            ach = vn_bytes / vn_avg / 1e9
-            roof = {"bound": "hbm", "kernel": vn_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "launches_sampled": n_s, "avg_launch_ms": 1e3 * vn_avg,
-                    "frame_iterations_per_launch": fi_per_launch,
+            vn_b = fi_per_launch * (2 * E_EDGES + N_VNS) / 8.0
+            cn_b = fi_per_launch * (2 * E_EDGES) / 8.0
+            ach = vn_b / vn_avg / 1e9
+            roof = {"bound": "hbm", "kernel": "bp_vn_stream_kernel<4>" if stream_mode else "bp_vn_wave_kernel<4,false>", "achieved": ach,
+                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tj.get("vn_sweep_dram_bytes_per_launch"), "peak_source": peak_src,
+                    "launches_sampled": n_s, "avg_launch_ms": 1e3 * vn_avg, "frame_iterations_per_launch": fi_per_launch,
                     "algorithmic_bytes": "(2E+n)/8 B per useful frame-iteration (reads E c2v bits + n channel bits, writes E v2c bits)"}
-            ach_c = cn_bytes / cn_avg / 1e9
-            kernels = {"bp_cn_wave_kernel<8,false>": {"achieved": ach_c, "frac": ach_c / peak, "unit": "GB/s", "avg_launch_ms": 1e3 * cn_avg,
-                                                      "algorithmic_bytes": "2E/8 B per useful frame-iteration"},
-                       "both_sweeps": {"achieved": (cn_bytes + vn_bytes) / (cn_avg + vn_avg) / 1e9,
-                                       "frac": (cn_bytes + vn_bytes) / (cn_avg + vn_avg) / 1e9 / peak, "unit": "GB/s"}}
+            kernels = {"bp_cn_wave_kernel<8,false>": {"achieved": cn_b / cn_avg / 1e9, "frac": cn_b / cn_avg / 1e9 / peak, "unit": "GB/s",
+                                                      "avg_launch_ms": 1e3 * cn_avg}}
 
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
-    h_vn = [fb.vn_cn.cpu().pin_memory() for fb in batches]
-    dims = batches[0].dims
+    # graph tables of every e2e step are drawn beforehand (on the device, copied to pinned host memory: untimed) -- each
+    # step uploads a set it has not seen, decodes fresh frame ids and downloads the per-frame results
+    dims = fb.dims
+    nw_e2e = min(2, args.warmup)
+    n_e2e = args.steps + nw_e2e
+    e2e_base = args.warmup + args.steps
+    h_vn = []
+    for j in range(n_e2e):
+        fb.generate_graphs(seed=args.seed, first_graph_id=gid_of(e2e_base + j))
+        h_vn.append(fb.vn_cn.cpu().pin_memory())
     if stream_mode:
         outs = [torch.zeros((G, B), dtype=torch.int32).pin_memory() for _ in range(5)]
-        cfgs = []
-        for fb in batches:
-            cfgs.append(_lib.StreamCfg(B, args.harvest_every, _lib.F_TERMINATED, 0, 0, eps_arr.ctypes.data_as(ctypes.c_void_p).value, None, None, None,
-                                       args.seed + 1, fb.gid0))
+        cfgs = [_lib.StreamCfg(B, args.harvest_every, _lib.F_TERMINATED | sflag, 0, 0, eps_arr.ctypes.data_as(ctypes.c_void_p).value, None, None, None,
+                               args.seed + 1, gid_of(e2e_base + j), 0) for j in range(n_e2e)]
         h2d = int(h_vn[0].numel() * 4)
         d2h = int(5 * G * B * 4)
-        api = "scldpc_stream_host (graph tables in pinned host memory; channel realisations drawn on the device)"
+        api = "scldpc_stream_host (graph tables in pinned host memory, a new set every step; channel realisations drawn on the device)"
 
-        def e2e_step(i):
-            _lib.check(lib.scldpc_stream_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[i % 2].data_ptr()), ctypes.byref(cfgs[i % 2]),
+        def e2e_step(j):
+            _lib.check(lib.scldpc_stream_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[j].data_ptr()), ctypes.byref(cfgs[j]),
                                               *[ctypes.c_void_p(o.data_ptr()) for o in outs], None))
             return int(outs[0].sum().item())
     else:
-        h_ch = [fb.chan.cpu().pin_memory() for fb in batches]
+        h_ch = []
+        for j in range(n_e2e):
+            fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid_of(e2e_base + j))
+            h_ch.append(fb.chan.cpu().pin_memory())
         outs = [torch.zeros((G, lanes), dtype=torch.int32).pin_memory() for _ in range(5)]
-        flags = _lib.F_TERMINATED | _lib.F_CHAN_PACKED
+        flags = _lib.F_TERMINATED | _lib.F_CHAN_PACKED | sflag
         h2d = int(h_vn[0].numel() * 4 + h_ch[0].numel() * 8)
         d2h = int(6 * G * lanes * 4)
         api = "scldpc_decode_host (graph tables + bit-sliced channel words in pinned host memory)"
 
-        def e2e_step(i):
-            _lib.check(lib.scldpc_decode_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[i % 2].data_ptr()),
-                                              ctypes.c_void_p(h_ch[i % 2].data_ptr()), 0, 0, 0, flags,
+        def e2e_step(j):
+            _lib.check(lib.scldpc_decode_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[j].data_ptr()),
+                                              ctypes.c_void_p(h_ch[j].data_ptr()), 0, 0, 0, flags,
                                               *[ctypes.c_void_p(o.data_ptr()) for o in outs], None, None, None, 0))
             return int(outs[0].sum().item())
 
-    for i in range(min(2, args.warmup)):
-        e2e_step(i)
+    for j in range(nw_e2e):
+        e2e_step(j)
     barrier()
     t0 = time.perf_counter()
     e_iters = 0
-    for i in range(args.steps):
-        e_iters += e2e_step(i)          # the call returns after its D2H copy has completed
+    for j in range(args.steps):
+        e_iters += e2e_step(nw_e2e + j)          # the call returns after its D2H copy has completed
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
     et = torch.tensor([e_dt], dtype=torch.float64, device=dev)
@@ -413,24 +709,38 @@ def run_ours(args):
     e2e = {"value": float(ei.item()) * 2.0 * E_EDGES / float(et.item()), "unit": "edge-updates/s",
            "frames_per_s": world * args.steps * G * B / float(et.item()),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api}
+    need = lib.scldpc_bp_stream_workspace_bytes(ctypes.byref(dims), sflag) if stream_mode else fb.workspace(_lib.F_TERMINATED | sflag).numel()
+    del fb, h_vn
+    torch.cuda.empty_cache()
+
+    workloads = None
+    if rank == 0 and world == 1 and args.workloads != "none":
+        try:
+            workloads = side_workloads(args, dev, side_cpu)
+        except Exception as e:  # pragma: no cover  (a side workload must never take the headline line down)
+            workloads = {"error": repr(e)}
 
     if rank == 0:
-        need = lib.scldpc_bp_stream_workspace_bytes(ctypes.byref(dims)) if stream_mode else batches[0].workspace(_lib.F_TERMINATED).numel()
         ws_mb = need / 2 ** 20
         line = {
             "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (64 bit-sliced frames per word)", "data": "synthetic",
-            "config": {"workload": WORKLOAD.replace("B frames", f"{B} frames"), "mode": args.mode, "sweeps": ("node-state" if os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") != "0" else "message passing"), "frames_per_step_per_gpu": G * B,
-                       "lanes_per_graph": lanes, "n_words": N_WORDS,
-                       "l2": f"inputs larger than L2: {ws_mb:.0f} MB of decoder state per batch, two batches alternated",
+            "config": {"workload": workload_name(B), "frames_per_graph": B, "graphs_per_step_per_gpu": G,
+                       "frames_per_step_per_gpu": G * B, "lanes_per_graph": lanes, "n_words": N_WORDS, "mode": args.mode,
+                       "sweeps": "message passing" if messages else "node-state",
+                       "graph_turnover": "new graphs every step, generated and indexed on the device inside the timed region; no "
+                                         "(graph, frame) realisation is decoded twice",
+                       "l2": f"inputs larger than L2: {ws_mb:.0f} MB of decoder state per batch, rewritten every step",
                        "seed": args.seed},
             "frames_per_s": frames / (ms * 1e-3),
             "frame_iterations_per_s": frame_iters / (ms * 1e-3),
             "mean_iterations_per_frame": frame_iters / max(1, frames),
             "frame_error_rate": ferr / max(1, frames), "bit_error_rate": berr / max(1, frames) / N_VNS,
+            "graph_generation": {"ms_per_generated_graph": graph_ms / max(1, args.steps * G), "share_of_step": graph_ms / max(1e-9, ms_local),
+                                 "what": "scldpc_graph_generate (Philox keys + bitonic sort per CN position) + scldpc_graph_build_tables, rank 0"},
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "kernels": kernels,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "workloads": workloads,
         }
         print(json.dumps(line))
     if world > 1:
@@ -439,7 +749,7 @@ def run_ours(args):
 
 
 def main():
-    global N_WORDS, FRAMES_PER_GRAPH, WORKLOAD
+    global N_WORDS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -449,14 +759,16 @@ def main():
     ap.add_argument("--graphs-per-eps", type=int, default=1)
     ap.add_argument("--sample-iters", type=int, default=10, help="reference arm: flooding iterations per sampled frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--side-baselines", action="store_true", help="reference arm: also time the CPU samples of the side workloads")
+    ap.add_argument("--workloads", default="all", help="side workloads at N=1: all | none | comma list of bp_full_fpg1024,"
+                                                       "bp_full_messages,bp_capped_175_traj,window_L100,peeling")
     ap.add_argument("--n-words", type=int, default=N_WORDS, help="64-bit lane words per node (lanes per graph / 64)")
     ap.add_argument("--mode", default="stream", choices=["stream", "batch"],
                     help="stream: lane recycling over --frames-per-graph frames per graph; batch: one frame per lane")
     ap.add_argument("--frames-per-graph", type=int, default=FRAMES_PER_STREAM)
-    ap.add_argument("--harvest-every", type=int, default=HARVEST_EVERY, help="stream mode: iterations between harvests of finished frames")
+    ap.add_argument("--harvest-every", type=int, default=0, help="stream mode: iterations between harvests (0: adaptive)")
     args = ap.parse_args()
     N_WORDS = args.n_words
-    FRAMES_PER_GRAPH = 64 * N_WORDS
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -547,7 +547,11 @@ __global__ void __launch_bounds__(256) bp_pos_count_kernel(BpParams p)
         }
     __syncthreads();
     for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
-        if (s_cnt[i]) atomicAdd(p.pos_cnt + ((size_t)g * p.L + pos) * p.lanes + i, s_cnt[i]);
+        if (s_cnt[i]) {
+            atomicAdd(p.pos_cnt + ((size_t)g * p.L + pos) * p.lanes + i, s_cnt[i]);
+            // node-state streams: "stopped with erased VNs left" is found here, not tracked per iteration
+            if (p.lazy_success) atomicOr(reinterpret_cast<unsigned long long *>(p.fail_mask + g * p.W + (i >> 6)), 1ull << (i & 63));
+        }
 }
 
 // Size-two stopping sets (BP_FULL.c:1075-1125): VNs a < b of one position, both erased, b on every CN of a, no
@@ -866,7 +870,11 @@ static void launch_count_pairs(const BpParams &p, cudaStream_t st)
 {
     int bx = (p.vns_pos * p.chunks + 255) / 256;
     if (bx > 8) bx = 8;
-    bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
+    if (p.lazy_success) {
+        BpParams q = p;
+        q.lane_mask = p.done_mask;                              // every stopped frame is counted; the failed ones land in fail_mask
+        bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(q);
+    } else bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
     dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, 4);
     if (p.ex2 && p.lane_mask) {
         g_prof.launches += 3;

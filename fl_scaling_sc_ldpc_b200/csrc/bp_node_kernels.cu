@@ -9,16 +9,25 @@
 // known).  The erased set -- hence the residual erasures, the per-frame iteration count under the
 // reference's stall rule (NumErasures == NumErasuresPrec, BP_FULL.c:1046-1066), the error counts and the expurgation
 // inputs -- is bit-identical to decodeBP's at every iteration; tests/test_stream_gpu.py holds it against the message
-// kernels (themselves checked against the oracle and the compiled reference).  What the formulation does not carry are
-// the messages, so the trajectory mode (deg_1_iter, BP_TRAJ.c:935-979) stays on the message kernels (bp_kernels.cu /
-// bp_wave_kernels.cu), which remain the implementation of record; the window decoder's node-state form is in bp_kernels.cu.
+// kernels (themselves checked against the oracle and the compiled reference) and tests/test_full_size_ref_gpu.py against
+// the compiled reference at the benchmarked size.  What the formulation does not carry are the messages, so the trajectory
+// mode (deg_1_iter, BP_TRAJ.c:935-979) stays on the message kernels (bp_kernels.cu / bp_wave_kernels.cu).
 //
-// State per graph: x and xb [n][chunks] (1 bit per VN and frame; equal between iterations).
-//   CN sweep  : gathers the dc x rows of a CN (E rows through L2: the gather stays inside a band of dv positions, 5 MB at
-//               M = 10000 and 1024 frames) and clears, in xb, the neighbour it resolves (sparse 32-bit atomics)
-//   state pass: sequential; copies the touched rows of xb to x, ORs "an erased VN is left", arms freed lanes
-// HBM sees the first touch of every x row, the index stream and the sequential state pass: about 2n/8 bytes per
-// frame-iteration (158 KB measured against 148 KB) instead of (4E + n)/8 = 1062 KB.
+// ONE launch per flooding iteration.  State per graph: two planes [n][chunks] (1 bit per VN and frame) that alternate as
+// "read" (the state after the previous iteration, which every CN of the sweep reads: that is the flooding schedule) and
+// "write" (where resolved bits are cleared).  Round 1 made the planes equal again with a sequential pass over the whole
+// plane after every sweep (41 % of an iteration: 69 MB streamed to move the ~6 % of rows that had changed).  Now every
+// warp of the sweep logs its resolutions -- (32-bit word of the plane, bit) -- into a private region, and the SAME warp
+// of the NEXT launch replays its region on that launch's write plane before it sweeps.  Clearing is commutative
+// (red.and), so the replay needs no ordering against the new resolutions, and nothing reads the write plane until the
+// launch after.  A region that overflows (the dense first iteration of a stream) raises a flag and the next launch
+// catches up with one full pass, so the lists never have to be sized for the worst case.
+//
+// "An erased VN is left" is no longer tracked per iteration either (it was the other reason for the full pass).  A frame
+// that resolves its last VN in iteration t is seen to stop in t+1 ("nothing resolved"); the harvest, which counts the
+// residual erasures of every stopped frame anyway, takes that extra iteration off again (lazy_success).  A frame that
+// stalls with erasures left stops in the iteration the reference stops in.  Iteration counts, residuals and every
+// derived statistic stay bit-identical; the ride-along iteration costs about 1/350 of the work.
 //
 // Useful work is still accounted as the reference's: 2E edge updates per frame-iteration.
 #include <cstdlib>
@@ -27,52 +36,103 @@
 
 namespace scldpc {
 
-constexpr int NS_X_ROWS = 4;
+__device__ __forceinline__ uint2 ld_cg_u2(const uint2 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cg_u2(uint2 *p, uint2 v)
+{
+    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// replay of one warp's region of the previous launch on plane `w` (32-bit words of graph g)
+__device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int par_prev, unsigned *w, int rid, bool zero_count)
+{
+    const int RW = NS_MAX_BLOCKS * NS_WARPS;
+    int *cntp = p.nl_cnt + (size_t)(g * 2 + par_prev) * RW + rid;
+    const int cnt = ld_cg(cntp);
+    const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * NS_WCAP;
+    for (int i = threadIdx.x & 31; i < cnt; i += 32) {
+        const uint2 e = ld_cg_u2(reg + i);
+        atomicAnd(w + e.x, ~e.y);
+    }
+    if (zero_count && (threadIdx.x & 31) == 0) *cntp = 0;
+}
+
+// catch-up after an overflow: w &= r on the whole plane (r is the plane the overflowing launch wrote, complete by now)
+__device__ __forceinline__ void ns_catch_up(const BpParams &p, const u128 *r, u128 *w)
+{
+    const int items = p.n << p.chunk_shift;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+        const u128 rv = ld_cg128(r + i), wv = ld_cg128(w + i);
+        const unsigned rr[4] = {(unsigned)rv.x, (unsigned)(rv.x >> 32), (unsigned)rv.y, (unsigned)(rv.y >> 32)};
+        const unsigned ww[4] = {(unsigned)wv.x, (unsigned)(wv.x >> 32), (unsigned)wv.y, (unsigned)(wv.y >> 32)};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (ww[q] & ~rr[q]) atomicAnd(reinterpret_cast<unsigned *>(w + i) + q, rr[q]);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------------
-// check-node sweep: a CN with exactly one erased neighbour (in x, the state after the previous iteration) resolves it --
-// the bit is cleared in xb, the copy that becomes the state after this iteration, so every CN of the sweep still reads the
-// old state (flooding).  Resolutions are sparse (a VN is resolved once per frame), so the scatter costs little.
-// The sweep is bound by L2 latency and instruction issue, not by HBM.  Measured and dropped: a cp.async pipeline for the
-// index rows (no gain, +25 % instructions), a register prefetch of the next index row (-8 %), five blocks per SM at 48
-// registers (-2 %).  The index of the neighbour to clear is carried in bit planes next to the saturating count, which
-// keeps the divergent scatter at ~30 instructions per resolution.
+// one flooding iteration: replay, check-node sweep, end of the iteration (last block)
 // ------------------------------------------------------------------------------------------------------------
+// CN sweep: a CN with exactly one erased neighbour in the read plane resolves it -- the bit is cleared in the write plane.
+// Resolutions are sparse (a VN is resolved once per frame; about 0.5 per thread and trip), so the scatter is a short divergent
+// loop; the index of the neighbour to clear is carried in bit planes next to the saturating count.
+// The sweep is bound by L2 latency and instruction issue, not by HBM.
 // CAPPED (streams with an iteration cap): a frame that hit the cap is not at a fixed point, so its bits must not be cleared
 // while it waits for the harvest -- the resolutions are masked with the frames still iterating.
 template <int DV, int DC, bool CAPPED>
-__global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
+__global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
     pdl_wait_then_release();
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
+    __shared__ int s_last;
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
     __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int par = p.iter & 1;
+    const size_t plane = (size_t)g * p.n * ch;
+    const u128 *__restrict__ rd = (par ? p.xb : p.x) + plane;
+    u128 *__restrict__ wr = (par ? p.x : p.xb) + plane;
+    unsigned *__restrict__ wr32 = reinterpret_cast<unsigned *>(wr);
+    const int RW = NS_MAX_BLOCKS * NS_WARPS;
+    const int rid = blockIdx.x * NS_WARPS + warp;
+
+    // ---- the write plane catches up with the previous iteration ----
+    if (ld_cg(p.nl_ovf + g * 2 + (par ^ 1))) ns_catch_up(p, rd, wr);
+    else ns_replay_region(p, g, par ^ 1, wr32, rid, false);
+
+    // ---- check-node sweep ----
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
     const bool lane_work = nz(act);                             // a thread keeps its chunk
-    const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
-    unsigned *__restrict__ xbk = reinterpret_cast<unsigned *>(p.xb + (size_t)g * p.n * ch + k);
-    unsigned char *__restrict__ dirtyk = p.dirty + (size_t)g * p.n * ch + k;
-    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
+    const u128 *__restrict__ rdk = rd + k;
+    const int32_t *__restrict__ cn_row = p.cn_row + (size_t)g * p.nk * DC;
+    uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * NS_WCAP;
     const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept
     const int stride = gridDim.x * blockDim.x;
-    const int E = p.E;
+    int wcount = 0;                                             // entries this warp has logged (warp-uniform)
     u128 acc_new = zero128();
-    if (lane_work)
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
-            const int32_t *row = cn_edge + (size_t)(idx >> p.chunk_shift) * DC;
+    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
+        const int idx = base + lane;
+        u128 res = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
+        const int32_t *row = cn_row + (size_t)(idx >> p.chunk_shift) * DC;
+        if (lane_work && idx < items) {
             int e[DC];
             load_row<DC>(row, e);
             u128 in[DC];
 #pragma unroll
-            for (int j = 0; j < DC; j++) in[j] = (e[j] != E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
+            for (int j = 0; j < DC; j++) in[j] = ld_cg128(rdk + (unsigned)e[j]);
             // saturating count of erased neighbours (one / two planes) and, in bit planes b0..b3, the index j of an erased
             // neighbour -- exact where it is needed, i.e. in the frames with exactly one
-            u128 one = zero128(), tw = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
+            u128 one = zero128(), tw = zero128();
 #pragma unroll
             for (int j = 0; j < DC; j++) {
                 tw |= one & in[j];
@@ -82,32 +142,49 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
                 if (j & 4) b2 |= in[j];
                 if (j & 8) b3 |= in[j];
             }
-            u128 res = one & ~tw;                               // frames in which exactly one neighbour of c is erased
+            res = one & ~tw;                                    // frames in which exactly one neighbour of c is erased
             if (CAPPED) res &= act;
-            if (nz(res)) {
-                acc_new |= res;
-                const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
-                const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
-                const unsigned w1[4] = {(unsigned)b1.x, (unsigned)(b1.x >> 32), (unsigned)b1.y, (unsigned)(b1.y >> 32)};
-                const unsigned w2[4] = {(unsigned)b2.x, (unsigned)(b2.x >> 32), (unsigned)b2.y, (unsigned)(b2.y >> 32)};
-                const unsigned w3[4] = {(unsigned)b3.x, (unsigned)(b3.x >> 32), (unsigned)b3.y, (unsigned)(b3.y >> 32)};
+        }
+        if (__ballot_sync(0xffffffffu, nz(res)) == 0u) continue;
+        // slots of this trip's resolutions in the warp's region: exclusive prefix sum of the per-thread counts
+        const int c = __popcll(res.x) + __popcll(res.y);
+        int incl = c;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    unsigned m = rw[q];
-                    while (m) {
-                        const int b = __ffs((int)m) - 1;
-                        m &= m - 1;
-                        int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
-                        if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
-                        const unsigned o = (unsigned)((__ldg(row + j) / DV) << p.chunk_shift);    // L1 hit
-                        atomicAnd(xbk + 4 * (size_t)o + q, ~(1u << b));
-                        dirtyk[o] = 1;
-                    }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int slot = wcount + incl - c;
+        wcount += __shfl_sync(0xffffffffu, incl, 31);
+        if (c) {
+            acc_new |= res;
+            const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
+            const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
+            const unsigned w1[4] = {(unsigned)b1.x, (unsigned)(b1.x >> 32), (unsigned)b1.y, (unsigned)(b1.y >> 32)};
+            const unsigned w2[4] = {(unsigned)b2.x, (unsigned)(b2.x >> 32), (unsigned)b2.y, (unsigned)(b2.y >> 32)};
+            const unsigned w3[4] = {(unsigned)b3.x, (unsigned)(b3.x >> 32), (unsigned)b3.y, (unsigned)(b3.y >> 32)};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                unsigned m = rw[q];
+                while (m) {
+                    const int b = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
+                    if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
+                    const unsigned widx = 4u * ((unsigned)__ldg(row + j) + (unsigned)k) + (unsigned)q;   // L1 hit
+                    atomicAnd(wr32 + widx, ~(1u << b));
+                    if (slot < NS_WCAP) st_cg_u2(reg + slot, make_uint2(widx, 1u << b));
+                    slot++;
                 }
             }
         }
+    }
+    if (lane == 0) {
+        p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < NS_WCAP ? wcount : NS_WCAP;
+        if (wcount > NS_WCAP) p.nl_ovf[g * 2 + par] = 1;
+    }
     acc_new = warp_or_same_chunk(acc_new, ch);
-    if ((threadIdx.x & 31) < ch) {
+    if (lane < ch) {
         if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
         if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
     }
@@ -116,106 +193,7 @@ __global__ void __launch_bounds__(256, 4) ns_cn_kernel(BpParams p)
         const int w = threadIdx.x;
         if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// state pass + end of the iteration (last block): brings x up to xb on the rows the CN sweep touched, collects "an erased
-// VN is left", arms freed lanes with their new frames' channel draws; same control flow as bp_vn_stream_kernel
-// ------------------------------------------------------------------------------------------------------------
-template <bool ARM, bool CAPPED>
-__global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
-{
-    pdl_wait_then_release();
-    // the CN sweep walks graphs and rows upwards, this pass downwards (vn_reverse): the CN sweep then starts on the rows
-    // this pass touched last -- its first gathers are L2 hits
-    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    if (ld_cg(p.alive + g) == 0) return;
-    __shared__ u64 s_er[SCLDPC_MAX_WORDS], s_first[SCLDPC_MAX_WORDS];
-    __shared__ int s_last;
-    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_er[threadIdx.x] = 0; s_first[threadIdx.x] = 0; }
-    __syncthreads();
-    const int ch = p.chunks;
-    const int k = threadIdx.x & (ch - 1);
-    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    const u128 arm = ARM ? reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k] : zero128();
-    u128 acc_er = zero128(), acc_first = zero128();
-    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
-    u128 *__restrict__ xb = p.xb + (size_t)g * p.n * ch;
-    unsigned char *__restrict__ dirty = p.dirty + (size_t)g * p.n * ch;
-    const int items = p.n << p.chunk_shift;
-    const int stride = gridDim.x * blockDim.x;
-    const u64 thr = (ARM && nz(arm)) ? p.thr[g] : 0ull;
-    const uint64_t gid = p.first_graph + (uint64_t)g;
-    constexpr int U = NS_X_ROWS;                                // rows in flight per thread: the pass is a plain stream
-    if (nz(act | arm))
-        for (int base = blockIdx.x * blockDim.x * U + threadIdx.x; base < items; base += stride * U) {
-            u128 xs[U];
-            unsigned char ds[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int lin = base + u * (int)blockDim.x;
-                const int idx = p.vn_reverse ? ((p.n - 1 - (lin >> p.chunk_shift)) << p.chunk_shift) + k : lin;
-                xs[u] = zero128(); ds[u] = 0;
-                if (lin < items) { xs[u] = ld_cg128(xb + idx); ds[u] = dirty[idx]; }   // the CN sweep wrote xb with atomics (L2)
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int lin = base + u * (int)blockDim.x;
-                if (lin >= items) break;
-                const int idx = p.vn_reverse ? ((p.n - 1 - (lin >> p.chunk_shift)) << p.chunk_shift) + k : lin;
-                u128 xn = xs[u];
-                const bool d = ds[u] != 0;
-                bool wr_x = d, wr_b = false;
-                if (ARM && nz(arm)) {
-                    // new frames: the erased set starts as the channel's (Lji = channel value on every edge, BP_FULL.c:913-917)
-                    const int v = idx >> p.chunk_shift;
-                    const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
-                    u128 cw = zero128();
-                    // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
-                    // usually shared by up to four armed lanes
-                    uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
-                    for (int half = 0; half < 2; half++) {
-                        u64 m = half ? arm.y : arm.x, w = 0;
-                        while (m && !forced) {
-                            const int b = __ffsll((long long)m) - 1;
-                            m &= m - 1;
-                            const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
-                            if ((fr >> 2) != blk) {
-                                blk = fr >> 2;
-                                philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
-                                              (uint32_t)(p.seed >> 32), r4);
-                            }
-                            if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
-                        }
-                        if (half) cw.y = w; else cw.x = w;
-                    }
-                    const u128 xa = sel(arm, cw, xn);
-                    if (neq(xa, xn)) { xn = xa; wr_x = true; wr_b = true; }
-                    acc_first |= ~cw & arm;                     // NumErasuresPrec = n before the first iteration: it makes
-                }                                               // "progress" iff the channel left some VN known
-                if (wr_x) x[idx] = xn;
-                if (wr_b) xb[idx] = xn;
-                if (d) dirty[idx] = 0;
-                acc_er |= xn & act;
-            }
-        }
-    acc_er = warp_or_same_chunk(acc_er, ch);
-    if (ARM) acc_first = warp_or_same_chunk(acc_first, ch);
-    if ((threadIdx.x & 31) < ch) {
-        if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
-        if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
-        if (ARM) {
-            if (acc_first.x) atomicOr(&s_first[2 * k], acc_first.x);
-            if (acc_first.y) atomicOr(&s_first[2 * k + 1], acc_first.y);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < p.W) {
-        const int w = threadIdx.x;
-        if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
-        if (ARM && (s_first[w] & ~ld_cg(p.first_new + g * p.W + w))) atomicOr(p.first_new + g * p.W + w, s_first[w]);
-        __threadfence();                                        // only these words are read by the graph's last block
-    }
+    __threadfence();                                            // list counts, overflow flag, any_new: read by the last block / next launch
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
     __syncthreads();
@@ -236,27 +214,123 @@ __global__ void __launch_bounds__(256, 4) ns_x_kernel(BpParams p)
     }
     __syncthreads();
     for (int w = threadIdx.x; w < W; w += blockDim.x) {
-        const u64 er = ld_cg(p.any_er + g * W + w);
-        p.any_er[g * W + w] = 0;
         const u64 a = s_act[w];
-        u64 nw = ld_cg(p.any_new + g * W + w);
-        if (!ARM) {                                             // lanes armed by the previous pass ran their first iteration
-            nw |= ld_cg(p.first_new + g * W + w);
-            p.first_new[g * W + w] = 0;
-        }
-        const u64 stop = a & (~er | ~nw | s_cap[w]);            // NumErasures == 0  ||  == NumErasuresPrec  ||  iteration cap
-        u64 left = a & ~stop;
-        if (ARM) { left |= p.arm_mask[g * W + w]; p.arm_mask[g * W + w] = 0; }   // armed lanes start iterating with the next sweep
-        p.active[g * W + w] = left;
+        // lanes armed by the last harvest run their first iteration: NumErasuresPrec = n, so it makes "progress" iff the
+        // channel left some VN known (first_new)
+        const u64 nw = ld_cg(p.any_new + g * W + w) | ld_cg(p.first_new + g * W + w);
+        const u64 stop = a & (~nw | s_cap[w]);                  // NumErasures == NumErasuresPrec (or == 0, one iteration late) || cap
+        p.active[g * W + w] = a & ~stop;
         p.done_mask[g * W + w] |= stop;
-        p.fail_mask[g * W + w] |= stop & er;
+        p.noprog[g * W + w] |= a & ~nw;
         p.any_new[g * W + w] = 0;
+        p.first_new[g * W + w] = 0;
     }
-    if (threadIdx.x == 0) p.ticket[g] = 0;
+    if (threadIdx.x == 0) {
+        p.nl_ovf[g * 2 + (par ^ 1)] = 0;                        // consumed by every block of this launch
+        p.ticket[g] = 0;
+    }
+}
+
+// Before a harvest: the plane the last iteration read catches up, so both planes are equal and the lists are empty
+// (lanes are re-armed with new frames right after; a replay after that would clear bits of the new frames).
+__global__ void __launch_bounds__(32 * NS_WARPS) ns_settle_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    const int par_prev = (p.iter & 1) ^ 1;                      // p.iter: the iteration that runs next
+    const size_t plane = (size_t)g * p.n * p.chunks;
+    const u128 *rd = ((p.iter & 1) ? p.xb : p.x) + plane;       // complete: the last iteration wrote it
+    u128 *wr = ((p.iter & 1) ? p.x : p.xb) + plane;
+    __shared__ int s_ovf;
+    if (threadIdx.x == 0) s_ovf = ld_cg(p.nl_ovf + g * 2 + par_prev);
+    __syncthreads();
+    if (s_ovf) ns_catch_up(p, rd, wr);
+    else ns_replay_region(p, g, par_prev, reinterpret_cast<unsigned *>(wr), blockIdx.x * NS_WARPS + (threadIdx.x >> 5), true);
+}
+__global__ void ns_settle_done_kernel(BpParams p)
+{
+    const int RW = NS_MAX_BLOCKS * NS_WARPS;
+    const int g = blockIdx.x, par_prev = (p.iter & 1) ^ 1;
+    if (ld_cg(p.nl_ovf + g * 2 + par_prev) == 0) return;
+    for (int i = threadIdx.x; i < RW; i += blockDim.x) p.nl_cnt[(size_t)(g * 2 + par_prev) * RW + i] = 0;
+    if (threadIdx.x == 0) p.nl_ovf[g * 2 + par_prev] = 0;
+}
+
+// After a harvest: the freed lanes take their new frames.  The erased set starts as the channel's (Lji = channel value on
+// every edge, BP_FULL.c:913-917), written to both planes; the lanes iterate from the next launch on.
+__global__ void __launch_bounds__(256, 4) ns_arm_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    if (ld_cg(p.alive + g) == 0) return;
+    __shared__ u64 s_first[SCLDPC_MAX_WORDS];
+    if (threadIdx.x < SCLDPC_MAX_WORDS) s_first[threadIdx.x] = 0;
+    __syncthreads();
+    const int ch = p.chunks;
+    const int k = threadIdx.x & (ch - 1);
+    const u128 arm = reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k];
+    u128 acc_first = zero128();
+    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u128 *__restrict__ xb = p.xb + (size_t)g * p.n * ch;
+    const int items = p.n << p.chunk_shift;
+    const u64 thr = p.thr[g];
+    const uint64_t gid = p.first_graph + (uint64_t)g;
+    if (nz(arm))
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += gridDim.x * blockDim.x) {
+            const int v = idx >> p.chunk_shift;
+            const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
+            u128 cw = zero128();
+            // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
+            // usually shared by up to four armed lanes
+            uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
+            for (int half = 0; half < 2; half++) {
+                u64 m = half ? arm.y : arm.x, w = 0;
+                while (m && !forced) {
+                    const int b = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
+                    if ((fr >> 2) != blk) {
+                        blk = fr >> 2;
+                        philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
+                                      (uint32_t)(p.seed >> 32), r4);
+                    }
+                    if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
+                }
+                if (half) cw.y = w; else cw.x = w;
+            }
+            const u128 xo = x[idx];
+            const u128 xn = sel(arm, cw, xo);
+            if (neq(xn, xo)) { x[idx] = xn; xb[idx] = xn; }
+            acc_first |= ~cw & arm;
+        }
+    acc_first = warp_or_same_chunk(acc_first, ch);
+    if ((threadIdx.x & 31) < ch) {
+        if (acc_first.x) atomicOr(&s_first[2 * k], acc_first.x);
+        if (acc_first.y) atomicOr(&s_first[2 * k + 1], acc_first.y);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.W) {
+        const int w = threadIdx.x;
+        if (s_first[w] & ~ld_cg(p.first_new + g * p.W + w)) atomicOr(p.first_new + g * p.W + w, s_first[w]);
+    }
+}
+
+// x-plane row offsets of the CN edges (once per stream call)
+__global__ void ns_cn_row_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    const size_t items = (size_t)p.nk * p.dc;
+    const int32_t *cn_edge = p.cn_edge + (size_t)g * items;
+    int32_t *cn_row = p.cn_row + (size_t)g * items;
+    // absent edges read the all-zero row that follows the last graph's plane
+    const unsigned zero_row = (unsigned)(((size_t)(p.G - g) * p.n) << p.chunk_shift);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = cn_edge[i];
+        cn_row[i] = (e != p.E) ? (int32_t)((unsigned)(e / p.dv) << p.chunk_shift) : (int32_t)zero_row;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// launcher
+// launchers
 // ------------------------------------------------------------------------------------------------------------
 template <typename K>
 static int resident_blocks_ns(K kernel, int block)
@@ -268,56 +342,84 @@ static int resident_blocks_ns(K kernel, int block)
     return occ * (sms > 0 ? sms : 148);
 }
 
+// every graph gets enough blocks to fill the machine on its own (blocks of finished graphs return at once); the same
+// geometry for every launch of a stream call, because a warp replays the region it wrote itself
 template <int DV, int DC>
-static void launch_node_iteration(const BpParams &p, bool arm, cudaStream_t st)
+static dim3 node_grid(const BpParams &p)
 {
-    const int block = 256;
-    static int res_cn = 0, res_x = 0;
-    if (!res_cn) {
-        res_cn = resident_blocks_ns(ns_cn_kernel<DV, DC, false>, block);
-        res_x = resident_blocks_ns(ns_x_kernel<true, false>, block);
+    const int block = 32 * NS_WARPS;
+    static int res = 0;
+    if (!res) {
+        res = resident_blocks_ns(ns_iter_kernel<DV, DC, false>, block);
+        if (res > NS_MAX_BLOCKS) res = NS_MAX_BLOCKS;
     }
-    // every graph gets enough blocks to fill the machine on its own: blocks of finished graphs return at once
-    auto grid = [&](int resident, long long items_per_graph) {
-        long long need = (items_per_graph + block - 1) / block;
-        long long gx = need < resident ? need : resident;
-        return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
-    };
-    dim3 gc = grid(res_cn, (long long)p.c1 << p.chunk_shift);
-    dim3 gx = grid(res_x, (((long long)p.n << p.chunk_shift) + NS_X_ROWS - 1) / NS_X_ROWS);
+    long long need = (((long long)p.cn_pos_lim * p.cns_pos << p.chunk_shift) + block - 1) / block;
+    long long gx = need < res ? need : res;
+    return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+}
+
+template <int DV, int DC>
+static void launch_node_iteration(const BpParams &p, bool after_harvest, cudaStream_t st)
+{
+    const dim3 block(32 * NS_WARPS), grid = node_grid<DV, DC>(p);
     const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
     cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
     if (sample) cudaEventRecord(ev[0], st);
-    g_prof.launches += 2;
+    g_prof.launches += 1;
     static const bool pdl = getenv("SCLDPC_NO_PDL") == nullptr;
-    // the first launch after a harvest (arm) follows ordinary kernels: full serialisation there
-    const bool capped = p.stream_cap > 0;
-    if (capped) launch_pdl(ns_cn_kernel<DV, DC, true>, gc, dim3(block), st, pdl && !arm && !sample, p);
-    else launch_pdl(ns_cn_kernel<DV, DC, false>, gc, dim3(block), st, pdl && !arm && !sample, p);
-    if (sample) cudaEventRecord(ev[1], st);
-    if (capped) {
-        if (arm) launch_pdl(ns_x_kernel<true, true>, gx, dim3(block), st, pdl && !sample, p);
-        else launch_pdl(ns_x_kernel<false, true>, gx, dim3(block), st, pdl && !sample, p);
-    } else {
-        if (arm) launch_pdl(ns_x_kernel<true, false>, gx, dim3(block), st, pdl && !sample, p);
-        else launch_pdl(ns_x_kernel<false, false>, gx, dim3(block), st, pdl && !sample, p);
-    }
+    // the first launch after a harvest follows ordinary kernels: full serialisation there
+    if (p.stream_cap > 0) launch_pdl(ns_iter_kernel<DV, DC, true>, grid, block, st, pdl && !after_harvest && !sample, p);
+    else launch_pdl(ns_iter_kernel<DV, DC, false>, grid, block, st, pdl && !after_harvest && !sample, p);
     if (sample) {
-        cudaEventRecord(ev[2], st);
+        cudaEventRecord(ev[1], st);
+        cudaEventRecord(ev[2], st);                             // one kernel per iteration: the second interval is empty
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
     }
 }
 
-// one iteration of every graph's frame stream; arm: lanes re-armed by the preceding harvest take their new frames
-int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st)
+// one iteration of every graph's frame stream; after_harvest: the launch follows the harvest kernels
+int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool after_harvest, cudaStream_t st)
 {
-    if (dv == 4 && dc == 8) launch_node_iteration<4, 8>(p, arm, st);
-    else if (dv == 3 && dc == 6) launch_node_iteration<3, 6>(p, arm, st);
-    else if (dv == 5 && dc == 10) launch_node_iteration<5, 10>(p, arm, st);
-    else if (dv == 3 && dc == 9) launch_node_iteration<3, 9>(p, arm, st);
-    else if (dv == 4 && dc == 12) launch_node_iteration<4, 12>(p, arm, st);
+    if (dv == 4 && dc == 8) launch_node_iteration<4, 8>(p, after_harvest, st);
+    else if (dv == 3 && dc == 6) launch_node_iteration<3, 6>(p, after_harvest, st);
+    else if (dv == 5 && dc == 10) launch_node_iteration<5, 10>(p, after_harvest, st);
+    else if (dv == 3 && dc == 9) launch_node_iteration<3, 9>(p, after_harvest, st);
+    else if (dv == 4 && dc == 12) launch_node_iteration<4, 12>(p, after_harvest, st);
     else return -1;
     return 0;
+}
+
+static dim3 node_grid_any(int dv, int dc, const BpParams &p)
+{
+    if (dv == 4 && dc == 8) return node_grid<4, 8>(p);
+    if (dv == 3 && dc == 6) return node_grid<3, 6>(p);
+    if (dv == 5 && dc == 10) return node_grid<5, 10>(p);
+    if (dv == 3 && dc == 9) return node_grid<3, 9>(p);
+    return node_grid<4, 12>(p);
+}
+
+// p.iter = the iteration that runs next; both planes equal and all lists empty afterwards
+void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 2;
+    ns_settle_kernel<<<node_grid_any(dv, dc, p), 32 * NS_WARPS, 0, st>>>(p);
+    ns_settle_done_kernel<<<p.G, 256, 0, st>>>(p);
+}
+
+void bp_launch_node_arm(const BpParams &p, cudaStream_t st)
+{
+    static int res = 0;
+    if (!res) res = resident_blocks_ns(ns_arm_kernel, 256);
+    long long need = (((long long)p.n << p.chunk_shift) + 255) / 256;
+    long long gx = need < res ? need : res;
+    g_prof.launches += 1;
+    ns_arm_kernel<<<dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G), 256, 0, st>>>(p);
+}
+
+void bp_launch_node_tables(const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    ns_cn_row_kernel<<<dim3(296, (unsigned)p.G), 256, 0, st>>>(p);
 }
 
 }  // namespace scldpc

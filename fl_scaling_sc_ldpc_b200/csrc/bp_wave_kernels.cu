@@ -558,7 +558,9 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
         const int fr = p.lane_frame[g * p.lanes + l];
         if (fr >= 0 && fr < B) {
             const size_t o = (size_t)g * B + fr;
-            const int its = p.lane_iter[g * p.lanes + l];
+            int its = p.lane_iter[g * p.lanes + l];
+            // node-state streams: a frame that finished was seen to stop one iteration late ("nothing resolved")
+            if (p.lazy_success && ((p.noprog[g * W + w] >> b) & 1ull) && !((p.fail_mask[g * W + w] >> b) & 1ull)) its -= 1;
             p.s_iters[o] = its;
             atomicAdd(&s_frames, 1);
             atomicAdd(&s_its, (unsigned long long)its);
@@ -585,6 +587,10 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
             p.fail_mask[g * W + w] = 0;
             p.arm_mask[g * W + w] = s_arm[w];
             any |= s_arm[w] | p.active[g * W + w];
+            if (p.lazy_success) {                               // ns_arm_kernel writes the new frames before the next iteration
+                p.active[g * W + w] |= s_arm[w];
+                p.noprog[g * W + w] = 0;
+            }
         }
         const int nn = next0 + s_rank[W];
         p.next_frame[g] = nn < B ? nn : B;

@@ -22,7 +22,10 @@ int bp_launch_window_persistent(int dv, int dc, const BpParams &p, int num_it, c
 int bp_launch_wave_iteration(int dv, int dc, const BpParams &p, bool traj, cudaStream_t st, int waves);
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st);
 int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
-int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool arm, cudaStream_t st);
+int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool after_harvest, cudaStream_t st);
+void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st);
+void bp_launch_node_arm(const BpParams &p, cudaStream_t st);
+void bp_launch_node_tables(const BpParams &p, cudaStream_t st);
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
 void bp_launch_window_node_init(const BpParams &p, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
@@ -41,6 +44,7 @@ void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
 int peel_grid(int total_size, long long total_frames);
 size_t peel_state_words(int n_cn_all, int total_size);
 int peel_launch(PeelParams p, int grid, cudaStream_t st);
+int ss_launch(const SsParams &p, cudaStream_t st);
 void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
                           long long *counts, cudaStream_t st);
 }  // namespace scldpc
@@ -65,6 +69,12 @@ static int fail(int code, const char *fmt, ...)
         cudaError_t e_ = (call);                                                                              \
         if (e_ != cudaSuccess) return fail(SCLDPC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                                            __FILE__, __LINE__);                                               \
+    } while (0)
+// after a group of kernel launches: the sticky runtime error and the first failed cudaLaunchKernelEx of this thread
+#define CU_LAUNCHES()                                                                                         \
+    do {                                                                                                      \
+        CU(cudaGetLastError());                                                                               \
+        CU(scldpc::take_launch_error());                                                                      \
     } while (0)
 
 static int check_dims(const scldpc_dims_t *d)
@@ -130,8 +140,9 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     Carve c{static_cast<char *>(ws), 0};
     BpParams q;
     memset(&q, 0, sizeof q);
-    // frame streams in node-state form (the default, see scldpc_bp_stream) keep no messages: 2 bits per edge less per frame
-    const bool no_msgs = (flags & SCLDPC_F_STREAM) && env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
+    // frame streams in node-state form (the default, see scldpc_bp_stream) keep no messages: 2 bits per edge less per frame.
+    // The layout depends on the flags alone (never on the environment): a size query and a call with the same flags agree.
+    const bool no_msgs = (flags & SCLDPC_F_STREAM) && !(flags & SCLDPC_F_MESSAGES);
     q.v2c = no_msgs ? nullptr : c.take<u128>(G * (E + 1) * ch);
     q.c2v = no_msgs ? nullptr : c.take<u128>(G * nk * d->dc * ch);
     q.latch = (flags & SCLDPC_F_TRAJECTORY) ? c.take<u128>(G * nk * ch) : nullptr;
@@ -164,11 +175,18 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.thr = c.take<u64>(G);
     q.known = c.take<int32_t>(d->L);
     if (flags & SCLDPC_F_STREAM) {
-        q.x = c.take<u128>(G * n * ch);                               // stream mode owns its decision plane
-        q.xb = c.take<u128>(G * n * ch);
+        q.x = c.take<u128>(G * n * ch + ch);                          // stream mode owns its decision plane; one all-zero row
+        q.xb = c.take<u128>(G * n * ch + ch);                         //   behind the last graph stands in for absent CN edges
         q.ex2 = c.take<u128>(G * nk * ch);
-        q.dirty = c.take<unsigned char>(G * n * ch);
         q.first_new = c.take<u64>(G * W);
+        if (no_msgs) {
+            const size_t RW = (size_t)NS_MAX_BLOCKS * NS_WARPS;
+            q.noprog = c.take<u64>(G * W);
+            q.cn_row = c.take<int32_t>(G * nk * d->dc);
+            q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
+            q.nl_cnt = c.take<int>(G * 2 * RW);
+            q.nl_ovf = c.take<int>(G * 2);
+        }
     }
     q.cn_dis = (flags & SCLDPC_F_STREAM) ? nullptr : c.take<u128>(G * nk * ch);   // sized for the largest possible ignored head
     if (p) *p = q;
@@ -381,7 +399,7 @@ static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool 
                             : (wave ? bp_launch_wave_iteration(dv, dc, *p, traj, st, waves) : bp_launch_iteration(dv, dc, *p, traj, freeze, st, bps)))
                 return fail(SCLDPC_EINVAL, "unsupported degrees");
         }
-        CU(cudaGetLastError());
+        CU_LAUNCHES();
         if (it >= cap) break;
         const int slot = nchunk & 1;
         CU(cudaMemcpyAsync(hf + slot, p->alive_total, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -399,20 +417,14 @@ static int run_iterations(BpParams *p, int dv, int dc, int cap, bool traj, bool 
     return 0;
 }
 
-// CNs [0, n) are "unscanned" in the next scldpc_bp_full calls of this thread (simulate_sc_ldpc with is_bounded = False:
-// slots below ignored_head_schedule*cns_per_pos are never scanned, PD.py:604-605,656); 0 switches it off.
-static thread_local int g_unscanned_cns = 0;
-extern "C" int scldpc_bp_set_unscanned_head(int n_cns)
-{
-    if (n_cns < 0) return fail(SCLDPC_EINVAL, "n_cns must be >= 0");
-    g_unscanned_cns = n_cns;
-    return 0;
-}
-
+// unscanned_head_cns: CNs [0, unscanned_head_cns) are "unscanned" (simulate_sc_ldpc with is_bounded = False: slots below
+// ignored_head_schedule*cns_per_pos are never scanned, PD.py:604-605,656); 0 = off.
 extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
-                              const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                              int unscanned_head_cns, const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                               int *iters_launched_host, void *stream)
 {
+    if (unscanned_head_cns < 0) return fail(SCLDPC_EINVAL, "unscanned_head_cns must be >= 0");
+    const int g_unscanned_cns = unscanned_head_cns;
     BpParams p;
     int rc = setup_params(d, b, flags, out, workspace_dev, workspace_bytes, &p);
     if (rc) return rc;
@@ -422,7 +434,7 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     // Error-rate runs (no trajectory) decode in node-state form: the window kernels of bp_kernels.cu with
     // one window that covers the whole code -- same erased set and stopping at every iteration as the message kernels,
     // which SCLDPC_FULL_NODE=0 selects and which trajectory mode always uses.
-    const bool node = !traj && d->n_frames > 0 && env_int("SCLDPC_FULL_NODE", 1, 0, 1) != 0;
+    const bool node = !traj && d->n_frames > 0 && !(flags & SCLDPC_F_MESSAGES);
     if (node) {
         p.xb = p.y;
         bp_launch_init_ctrl_only(p, d->n_frames, st);
@@ -437,7 +449,7 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     p.win_edges = 2ll * p.E;
     int launched = 0;
     // wave tracking (bp_wave_kernels.cu) unless disabled or the chain is longer than its shared-memory bitmaps
-    const bool wave = !node && d->L + d->dv - 1 <= 1024 && (!env_int("SCLDPC_NO_WAVE", 0, 0, 1) || g_unscanned_cns > 0);
+    const bool wave = !node && d->L + d->dv - 1 <= 1024 && (!(flags & SCLDPC_F_NO_WAVE) || g_unscanned_cns > 0);
     p.cn_dis_lim = g_unscanned_cns;
     if (g_unscanned_cns > 0 && ((!wave && !node) || traj || g_unscanned_cns > p.nk))
         return fail(SCLDPC_EINVAL, "unscanned head: not available with trajectories or for this chain length");
@@ -453,10 +465,10 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     return 0;
 }
 
-extern "C" size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d)
+extern "C" size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d, uint32_t flags)
 {
     if (check_dims(d)) return 0;
-    return carve(d, SCLDPC_F_STREAM, nullptr, nullptr);
+    return carve(d, SCLDPC_F_STREAM | (flags & SCLDPC_F_MESSAGES), nullptr, nullptr);
 }
 
 // Full BP (unlimited iterations) over a stream of cfg->frames_per_graph frames per graph with lane recycling.
@@ -472,14 +484,18 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     if (!out || !out->iters_dev || !out->residual_dev || !out->blocks_err_dev || !out->erasures_exp_dev || !out->blocks_err_exp_dev)
         return fail(SCLDPC_EINVAL, "output pointer is NULL");
     if (d->n_frames < 1) return fail(SCLDPC_EINVAL, "n_frames (lanes used per graph) must be >= 1");
-    if (d->L + d->dv - 1 > 1024) return fail(SCLDPC_EINVAL, "chain too long for stream mode");
+    if ((cfg->flags & SCLDPC_F_MESSAGES) && d->L + d->dv - 1 > 1024) return fail(SCLDPC_EINVAL, "chain too long for the message-passing stream");
     if (!workspace_dev) return fail(SCLDPC_EINVAL, "workspace is NULL");
-    const size_t need = carve(d, SCLDPC_F_STREAM, nullptr, nullptr);
+    // SCLDPC_F_MESSAGES selects the message-passing sweeps (the implementation of record); the default is the node-state
+    // formulation of bp_node_kernels.cu, which yields the same erased set at every iteration with ~6x less HBM traffic
+    const bool node = !(cfg->flags & SCLDPC_F_MESSAGES);
+    const uint32_t wflags = SCLDPC_F_STREAM | (cfg->flags & SCLDPC_F_MESSAGES);
+    const size_t need = carve(d, wflags, nullptr, nullptr);
     if (workspace_bytes < need) return fail(SCLDPC_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
     if ((rc = have_device())) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     BpParams p;
-    carve(d, SCLDPC_F_STREAM, workspace_dev, &p);
+    carve(d, wflags, workspace_dev, &p);
     p.dv = d->dv; p.dc = d->dc;
     p.n = d->L * d->vns_pos; p.nk = (d->L + d->dv - 1) * d->cns_pos; p.E = p.n * d->dv;
     p.L = d->L; p.vns_pos = d->vns_pos; p.cns_pos = d->cns_pos;
@@ -487,6 +503,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     p.n_valid = d->n_frames;
     p.chunk_shift = 0;
     while ((1 << p.chunk_shift) < p.chunks) p.chunk_shift++;
+    if (node && ((size_t)p.G * p.n + 1) * p.chunks * 4 >= (size_t)1 << 32)
+        return fail(SCLDPC_EINVAL, "batch too large for 32-bit plane offsets: reduce n_graphs");
     p.vn_cn = b->vn_cn_dev; p.vn_slot = b->vn_slot_dev; p.cn_edge = b->cn_edge_dev; p.chan = nullptr;
     p.iters = p.lane_iter;                       // scratch for the shared control initialisation
     p.rows = nullptr; p.max_rows = 0; p.row = -1;
@@ -500,6 +518,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     p.s_erasures_exp = out->erasures_exp_dev; p.s_blocks_err_exp = out->blocks_err_exp_dev;
     p.vn_reverse = env_int("SCLDPC_VN_REVERSE", 1, 0, 1);
     p.lane_mask = p.fail_mask;                   // frames that stopped without erasures have all-zero counts already
+    p.lazy_success = node ? 1 : 0;
     // per-graph channel thresholds and the doping profile
     std::vector<u64> thr(d->n_graphs);
     for (int g = 0; g < d->n_graphs; g++) {
@@ -514,17 +533,18 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     if (doped) CU(cudaMemcpyAsync(const_cast<int32_t *>(p.known), known.data(), sizeof(int32_t) * d->L, cudaMemcpyHostToDevice, st));
     else p.known = nullptr;
     CU(cudaStreamSynchronize(st));               // host vectors leave scope at return; keep it simple
-    // state: Lij = 1 (tail CNs of a truncated code are never swept), everything else 0; no lane holds a frame yet
-    const size_t ch = p.chunks;
-    // SCLDPC_STREAM_NODE=0 selects the message-passing sweeps (the implementation of record); the default is the node-state
-    // formulation of bp_node_kernels.cu, which yields the same erased set at every iteration with ~6x less HBM traffic
-    const bool node = env_int("SCLDPC_STREAM_NODE", 1, 0, 1) != 0;
-    if (!node && p.stream_cap > 0) return fail(SCLDPC_EINVAL, "capped frame streams need the node-state sweeps (SCLDPC_STREAM_NODE=1)");
-    CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
+    if (!node && p.stream_cap > 0) return fail(SCLDPC_EINVAL, "capped frame streams need the node-state sweeps (no SCLDPC_F_MESSAGES)");
+    // state: no lane holds a frame yet.  Message sweeps: Lij = 1 (tail CNs of a truncated code are never swept), the rest 0
+    const size_t ch = p.chunks, plane = ((size_t)p.G * p.n + 1) * ch;
+    CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * plane, st));
+    CU(cudaMemsetAsync(p.first_new, 0, sizeof(u64) * (size_t)p.G * p.W, st));
     if (node) {
-        CU(cudaMemsetAsync(p.xb, 0, sizeof(u128) * (size_t)p.G * p.n * ch, st));
-        CU(cudaMemsetAsync(p.dirty, 0, (size_t)p.G * p.n * ch, st));
-        CU(cudaMemsetAsync(p.first_new, 0, sizeof(u64) * (size_t)p.G * p.W, st));
+        const size_t RW = (size_t)NS_MAX_BLOCKS * NS_WARPS;
+        CU(cudaMemsetAsync(p.xb, 0, sizeof(u128) * plane, st));
+        CU(cudaMemsetAsync(p.noprog, 0, sizeof(u64) * (size_t)p.G * p.W, st));
+        CU(cudaMemsetAsync(p.nl_cnt, 0, sizeof(int) * (size_t)p.G * 2 * RW, st));
+        CU(cudaMemsetAsync(p.nl_ovf, 0, sizeof(int) * (size_t)p.G * 2, st));
+        bp_launch_node_tables(p, st);
     } else {
         CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
         CU(cudaMemsetAsync(p.v2c, 0, sizeof(u128) * (size_t)p.G * (p.E + 1) * ch, st));
@@ -534,10 +554,11 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         BpParams q = p;                          // control words, counters, position lists ("every position")
         bp_launch_init_ctrl_only(q, d->n_frames, st);
     }
-    bp_launch_wave_init(p, st);
+    if (!node) bp_launch_wave_init(p, st);
     bp_launch_stream_init(p, d->n_frames, st);
     bp_launch_stream_harvest(p, 0, st);          // arms the first frames
-    CU(cudaGetLastError());
+    if (node) bp_launch_node_arm(p, st);
+    CU_LAUNCHES();
     int *hf = nullptr;
     if ((rc = host_flag(&hf))) return rc;
     static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -564,10 +585,13 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         }
         const int slot = nchunk & 1;
         p.harvest_parity = slot;
+        p.iter = (int)(it & 0x3fffffff);         // the iteration that runs next (its parity names the planes)
         if (adaptive) CU(cudaMemsetAsync(p.alive_total + 1 + slot, 0, sizeof(int), st));
+        if (node) bp_launch_node_settle(d->dv, d->dc, p, st);
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
-        CU(cudaGetLastError());
+        if (node) bp_launch_node_arm(p, st);
+        CU_LAUNCHES();
         CU(cudaMemcpyAsync(hf + 4 * slot, p.alive_total, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
         pending[slot] = true;
@@ -604,9 +628,9 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
     const int ms = d->dv - 1, L = d->L, vp = d->vns_pos, cp = d->cns_pos;
     const int nwin = square ? L : L + ms;                          // BP_SW.c:672 / BP_FULL.c:668
     const int cn_clip = term ? p.nk : L * cp;
-    // SCLDPC_WINDOW_NODE=0 selects the message-passing sweeps (the implementation of record); the default is their node-state
+    // SCLDPC_F_MESSAGES selects the message-passing sweeps (the implementation of record); the default is their node-state
     // form (bpw_*_node_kernel in bp_kernels.cu): same decisions, counters and per-window stopping, about a third of the traffic
-    const bool node = env_int("SCLDPC_WINDOW_NODE", 1, 0, 1) != 0 && d->n_frames > 0;
+    const bool node = !(flags & SCLDPC_F_MESSAGES) && d->n_frames > 0;
     if (node) {
         p.xb = p.y;                                                // the wave-tracking plane is free in window mode
         bp_launch_init_ctrl_only(p, d->n_frames, st);
@@ -737,6 +761,42 @@ extern "C" int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags,
     return 0;
 }
 
+// ---- stopping sets of the residual graph (simulate_sc_ldpc, PD.py:659-691 + extract_stopping_sets PD.py:1077-1095) ----
+extern "C" int scldpc_bp_stopping_sets(const scldpc_dims_t *d, const scldpc_batch_t *b, const uint64_t *erased_dev,
+                                       const uint8_t *counted_pos_host, int32_t *out_dev, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!degrees_supported(d->dv, d->dc)) return fail(SCLDPC_EINVAL, "(dv,dc)=(%d,%d) not instantiated", d->dv, d->dc);
+    if (!b || !b->vn_cn_dev || !b->cn_edge_dev || !erased_dev || !out_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SsParams p;
+    memset(&p, 0, sizeof p);
+    p.dv = d->dv; p.dc = d->dc; p.n = d->L * d->vns_pos; p.nk = (d->L + d->dv - 1) * d->cns_pos; p.E = p.n * d->dv;
+    p.L = d->L; p.vns_pos = d->vns_pos; p.G = d->n_graphs; p.W = d->n_words; p.chunks = d->n_words / 2; p.lanes = 64 * d->n_words;
+    while ((1 << p.chunk_shift) < p.chunks) p.chunk_shift++;
+    p.vn_cn = b->vn_cn_dev; p.cn_edge = b->cn_edge_dev; p.x = reinterpret_cast<const u128 *>(erased_dev); p.out = out_dev;
+    const size_t cnt_bytes = sizeof(int) * (size_t)p.G * p.L * p.lanes, ge3_bytes = sizeof(u128) * (size_t)p.G * p.nk * p.chunks;
+    char *scratch = nullptr;
+    const size_t cnt_al = align_up(cnt_bytes), L_al = align_up((size_t)d->L);
+    CU(cudaMallocAsync(&scratch, 2 * cnt_al + ge3_bytes + L_al, st));
+    p.pos_lost = reinterpret_cast<int *>(scratch);
+    p.pos_big = reinterpret_cast<int *>(scratch + cnt_al);
+    p.ge3 = reinterpret_cast<u128 *>(scratch + 2 * cnt_al);
+    unsigned char *counted = reinterpret_cast<unsigned char *>(scratch + 2 * cnt_al + ge3_bytes);
+    p.counted = counted;
+    CU(cudaMemsetAsync(scratch, 0, 2 * cnt_al, st));
+    std::vector<unsigned char> cp(d->L, 1);
+    if (counted_pos_host) cp.assign(counted_pos_host, counted_pos_host + d->L);
+    CU(cudaMemcpyAsync(counted, cp.data(), d->L, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));               // cp leaves scope
+    if (ss_launch(p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+    CU_LAUNCHES();
+    CU(cudaFreeAsync(scratch, st));
+    return 0;
+}
+
 // ---- instrumentation --------------------------------------------------------------------------------------------
 // Positions swept by the last scldpc_bp_full call on this workspace, summed over graphs and iterations:
 // out[0] = CN positions, out[1] = VN positions (a sweep of everything would be iterations*(L+dv-1) and iterations*L).
@@ -838,7 +898,7 @@ extern "C" int scldpc_stream_host(const scldpc_dims_t *d, const int32_t *vn_cn_h
     const size_t G = d->n_graphs, B = cfg->frames_per_graph > 0 ? cfg->frames_per_graph : 0;
     const size_t n = (size_t)d->L * d->vns_pos, nk = (size_t)(d->L + d->dv - 1) * d->cns_pos, E = n * d->dv;
     DevBuf vn_cn, vn_slot, cn_edge, scratch, ws, res;
-    const size_t ws_bytes = scldpc_bp_stream_workspace_bytes(d);
+    const size_t ws_bytes = scldpc_bp_stream_workspace_bytes(d, cfg->flags);
     if (vn_cn.alloc(4 * G * E) || vn_slot.alloc(4 * G * E) || cn_edge.alloc(4 * G * nk * d->dc) || scratch.alloc(4 * G * nk) ||
         ws.alloc(ws_bytes) || res.alloc(4 * 5 * G * B))
         return fail(SCLDPC_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -889,7 +949,7 @@ extern "C" int scldpc_decode_host(const scldpc_dims_t *d, const int32_t *vn_cn_h
     scldpc_bp_out_t out{r, r + G * lanes, r + 2 * G * lanes, r + 3 * G * lanes, r + 4 * G * lanes, r + 5 * G * lanes,
                         static_cast<uint64_t *>(xbuf.p), traj ? static_cast<int32_t *>(rows.p) : nullptr, traj ? max_rows : 0};
     if (traj) CU(cudaMemsetAsync(rows.p, 0, 4 * 3 * G * (size_t)max_rows * lanes, st));
-    if (W == 0) rc = scldpc_bp_full(d, &b, max_it, kflags, &out, ws.p, ws_bytes, nullptr, st);
+    if (W == 0) rc = scldpc_bp_full(d, &b, max_it, kflags, 0, &out, ws.p, ws_bytes, nullptr, st);
     else rc = scldpc_bp_window(d, &b, W, max_it, init_it, kflags & ~SCLDPC_F_TRAJECTORY, &out, ws.p, ws_bytes, nullptr, st);
     if (rc) return rc;
     std::vector<int32_t> h(6 * G * lanes);

@@ -12,6 +12,10 @@ typedef ulonglong2 u128;   // one 16-byte chunk = 128 bit-sliced frames
 // per-lane trajectory counters are spread over this many slots (blockIdx.x % slots) so that the blocks' final atomicAdds do
 // not all hit the same 64*W addresses; the retire step sums the slots
 #define SCLDPC_CNT_SLOTS 4
+// node-state frame streams (bp_node_kernels.cu): geometry of the per-warp resolution lists
+#define NS_WARPS 8            // warps per block of the sweep
+#define NS_MAX_BLOCKS 640     // blocks per graph of the sweep (>= 4 resident blocks x 148 SMs)
+#define NS_WCAP 1024          // list entries per warp and iteration; beyond that the iteration is caught up by a full pass
 
 __device__ __forceinline__ u128 make_u128(u64 a, u64 b) { u128 r; r.x = a; r.y = b; return r; }
 __device__ __forceinline__ u128 operator|(u128 a, u128 b) { return make_u128(a.x | b.x, a.y | b.y); }
@@ -226,10 +230,18 @@ struct BpParams {
     // frame streams (lane recycling): a finished frame frees its bit lane for the next channel realisation
     u64 *arm_mask;            // [G][W] lanes that take a new frame in the next VN sweep
     u64 *done_mask;           // [G][W] lanes whose frame has stopped and waits to be harvested
-    u128 *xb;                 // [G][n][chunks] node-state streams: the erased set being built by this iteration's CN sweep (bp_node_kernels.cu)
-    unsigned char *dirty;     // [G][n*chunks] node-state streams: rows of xb the CN sweep cleared bits in
+    u128 *xb;                 // [G][n][chunks] node-state decoders: second plane (streams: x and xb alternate as read / write plane, bp_node_kernels.cu)
     u128 *ex2;                // [G][nk][chunks] frame streams: "exactly two erased neighbours" plane of the harvest (NULL: one-pass pairs kernel)
     u64 *first_new;           // [G][W] node-state streams: lanes whose new frame has a VN the channel left known
+    u64 *noprog;              // [G][W] node-state streams: lanes that stopped because an iteration resolved nothing (see bp_node_kernels.cu)
+    int32_t *cn_row;          // [G][nk][dc] node-state streams: x-plane row offset (v << chunk_shift) of each CN edge; absent edges
+                              //   point at the all-zero row behind the last graph's plane
+    uint2 *nl_list;           // [G][2][NS_MAX_BLOCKS*NS_WARPS][NS_WCAP] node-state streams: (32-bit word of the plane, bits cleared) per
+                              //   resolution of the previous iteration, one private region per warp of the sweep's grid
+    int *nl_cnt;              // [G][2][NS_MAX_BLOCKS*NS_WARPS] entries in each region
+    int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
+    int lazy_success;         // 1: "no erased VN is left" is not tracked per iteration; a frame that finishes stops one iteration
+                              //   later on "nothing resolved" and the harvest takes that iteration off again
     u64 *fail_mask;           // [G][W] subset of done_mask that stopped with erased VNs left (the only lanes the count kernels read)
     int *lane_frame;          // [G][lanes] frame id decoded in the lane, -1 if idle
     int *lane_iter;           // [G][lanes] iterations executed by the lane's current frame
@@ -276,6 +288,18 @@ struct PeelParams {
     uint64_t seed, first_frame;
 };
 
+// Parameter block of the stopping-set kernels (ss_kernels.cu).
+struct SsParams {
+    int dv, dc, n, nk, E, L, vns_pos, G, W, chunks, chunk_shift, lanes;
+    const int32_t *vn_cn;      // [G][n][dv]
+    const int32_t *cn_edge;    // [G][nk][dc]
+    const u128 *x;             // [G][n][chunks] erased VNs after decoding
+    const unsigned char *counted;   // [L] 1: VNs of the position can be lost (PD.py:661-666)
+    u128 *ge3;                 // [G][nk][chunks]
+    int *pos_lost, *pos_big;   // [G][L][lanes]
+    int32_t *out;              // [G][lanes][4]
+};
+
 // Programmatic dependent launch: the two node-state kernels of an iteration follow each other ~10^5 times per decode, so the launch
 // gap between them is worth hiding.  Every block first waits for the predecessor grid (nothing it wrote is read before
 // that), then lets the successor's blocks be scheduled as soon as all blocks of this grid have started; those blocks sit
@@ -286,6 +310,21 @@ __device__ __forceinline__ void pdl_wait_then_release()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// first failed launch of this thread since the last scldpc_take_launch_error(); the C ABI turns it into SCLDPC_ECUDA
+namespace scldpc {
+inline cudaError_t &launch_error_slot()
+{
+    static thread_local cudaError_t e = cudaSuccess;
+    return e;
+}
+inline cudaError_t take_launch_error()
+{
+    cudaError_t e = launch_error_slot();
+    launch_error_slot() = cudaSuccess;
+    return e;
+}
+}  // namespace scldpc
+
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args)
 {
@@ -295,7 +334,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, args...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess && scldpc::launch_error_slot() == cudaSuccess) scldpc::launch_error_slot() = e;
 }
 
 

@@ -15,9 +15,20 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import F_EXP_ALL, F_SQUARE, F_TERMINATED, F_TRAJECTORY
+import os
+
+from ._lib import F_EXP_ALL, F_MESSAGES, F_NO_WAVE, F_SQUARE, F_TERMINATED, F_TRAJECTORY
 
 UNLIMITED = 0  # max_it value meaning "until every frame has stalled or finished"
+
+
+def _sweep_flags(env_name: str, messages: bool | None) -> int:
+    """Implementation selector -> C-ABI flag.  ``messages=None`` takes the default from the environment variable (0 selects
+    the message-passing sweeps); the library itself never reads the environment for this, so a workspace-size query and a
+    decoder call always agree."""
+    if messages is None:
+        messages = os.environ.get(env_name, "1") == "0"
+    return F_MESSAGES if messages else 0
 
 
 @dataclass(frozen=True)
@@ -217,11 +228,16 @@ def _collect(fb: FrameBatch, res, erased, rows, **kw) -> BpResult:
 
 
 def decode_bp_full(fb: FrameBatch, max_it: int = UNLIMITED, is_term: bool = True, trajectory: bool = False,
-                   max_rows: int | None = None, collect: bool = True):
+                   max_rows: int | None = None, collect: bool = True, unscanned_head_cns: int = 0,
+                   messages: bool | None = None):
     """Full flooding BP -- ``decodeBP`` (BP_FULL.c:900, BP_TRAJ.c:901).  ``max_it`` is the reference's ``MaxNumIt``
     (values <= 0 run until every frame has stalled or finished; note the reference's do-while executes at least one
-    iteration, which callers reproduce by passing max(1, MaxNumIt))."""
-    flags = (F_TERMINATED if is_term else 0) | (F_TRAJECTORY if trajectory else 0)
+    iteration, which callers reproduce by passing max(1, MaxNumIt)).  ``unscanned_head_cns``: CNs below this index are
+    never scanned (``simulate_sc_ldpc`` with ``is_bounded=False``, PD.py:604-605,656).  ``messages``: pass explicit messages
+    instead of the node-state sweeps (default from ``SCLDPC_FULL_NODE``; trajectories always pass messages)."""
+    flags = (F_TERMINATED if is_term else 0) | (F_TRAJECTORY if trajectory else 0) | _sweep_flags("SCLDPC_FULL_NODE", messages)
+    if os.environ.get("SCLDPC_NO_WAVE", "0") == "1":
+        flags |= F_NO_WAVE
     if trajectory and not max_rows:
         if max_it <= 0:
             raise ValueError("trajectory mode needs max_rows when max_it is unlimited")
@@ -229,7 +245,7 @@ def decode_bp_full(fb: FrameBatch, max_it: int = UNLIMITED, is_term: bool = True
     res, erased, rows, out = _alloc_out(fb, max_rows if trajectory else 0)
     ws = fb.workspace(flags)
     launched = ctypes.c_int(0)
-    _lib.check(_lib.lib().scldpc_bp_full(ctypes.byref(fb.dims), ctypes.byref(fb.cbatch), int(max_it), flags, ctypes.byref(out),
+    _lib.check(_lib.lib().scldpc_bp_full(ctypes.byref(fb.dims), ctypes.byref(fb.cbatch), int(max_it), flags, int(unscanned_head_cns), ctypes.byref(out),
                                          ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), ctypes.byref(launched),
                                          _stream()))
     if not collect:
@@ -251,9 +267,9 @@ def position_counts(fb: FrameBatch, flags: int):
 
 
 def decode_bp_window(fb: FrameBatch, W: int, max_it: int, init_it: int = 0, square: bool = True, is_term: bool = True,
-                     collect: bool = True):
+                     collect: bool = True, messages: bool | None = None):
     """Sliding-window BP -- ``decodeBP_SW`` (square window BP_SW.c:628, classical window BP_FULL.c:627)."""
-    flags = (F_TERMINATED if is_term else 0) | (F_SQUARE if square else 0) | F_EXP_ALL
+    flags = (F_TERMINATED if is_term else 0) | (F_SQUARE if square else 0) | F_EXP_ALL | _sweep_flags("SCLDPC_WINDOW_NODE", messages)
     res, erased, rows, out = _alloc_out(fb, 0)
     ws = fb.workspace(flags)
     work = ctypes.c_int64(0)
@@ -278,7 +294,8 @@ class StreamResult:
 
 
 def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, first_graph_id: int = 0, is_term: bool = True,
-                     doping_points=(), harvest_every: int = 0, exp_all: bool = False, collect: bool = True, max_it: int = 0):
+                     doping_points=(), harvest_every: int = 0, exp_all: bool = False, collect: bool = True, max_it: int = 0,
+                     messages: bool | None = None):
     """Full BP (unlimited, or at most ``max_it`` iterations per frame) over a stream of ``frames_per_graph`` frames per
     graph with lane recycling (``scldpc_bp_stream``).  Frame f of graph g is the channel realisation ``generate_erasures(..., first_frame=...)``
     puts in lane f - first_frame; the graphs are the ones resident in ``fb`` (``fb.n_frames`` lanes are used)."""
@@ -295,12 +312,12 @@ def decode_bp_stream(fb: FrameBatch, frames_per_graph: int, eps, seed: int, firs
     arr = lambda xs: np.asarray(xs or [0], np.int32)
     a_h, a_sp, a_sc = arr(hard), arr(soft_p), arr(soft_c)
     ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p).value
-    flags = (F_TERMINATED if is_term else 0) | (F_EXP_ALL if exp_all else 0)
+    flags = (F_TERMINATED if is_term else 0) | (F_EXP_ALL if exp_all else 0) | _sweep_flags("SCLDPC_STREAM_NODE", messages)
     cfg = _lib.StreamCfg(B, int(harvest_every), flags, len(hard), len(soft_p), ptr(eps_arr), ptr(a_h), ptr(a_sp), ptr(a_sc),
                          int(seed), int(first_graph_id), max(0, int(max_it)))
     res = torch.zeros((5, G, B), dtype=torch.int32, device=fb.device)
     out = _lib.StreamOut(*[res[i].data_ptr() for i in range(5)])
-    need = L.scldpc_bp_stream_workspace_bytes(ctypes.byref(fb.dims))
+    need = L.scldpc_bp_stream_workspace_bytes(ctypes.byref(fb.dims), flags)
     if need == 0:
         raise _lib.ScldpcError(L.scldpc_last_error().decode())
     if fb._ws is None or fb._ws.numel() < need:

@@ -213,6 +213,17 @@ def account_lost(lost: np.ndarray, transmissions: np.ndarray, M: int):
     return len(lost), int(len(big) > 0), sum(len(s) for s in big), len(lost_exp)
 
 
+def stopping_set_records(fb, erased_words, counted) -> np.ndarray:
+    """``scldpc_bp_stopping_sets``: int32 [G][64*n_words][4] = (num_lost, has a stopping set of more than two VNs, VNs in
+    such sets, VN positions they touch) per frame -- what ``account_lost`` returns, for every frame of the batch at once."""
+    out = torch.empty((fb.n_graphs, 64 * fb.n_words, 4), dtype=torch.int32, device=fb.device)
+    cp = np.ascontiguousarray(np.asarray(counted, dtype=np.uint8))
+    assert cp.shape == (fb.ens.L,)
+    _lib.check(_lib.lib().scldpc_bp_stopping_sets(ctypes.byref(fb.dims), ctypes.byref(fb.cbatch), ctypes.c_void_p(erased_words.data_ptr()),
+                                                 cp.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(out.data_ptr()), engine._stream()))
+    return out.cpu().numpy()
+
+
 def counted_positions(l, L, num_positions, ignored_head, ignored_tail, is_tail_biting=False) -> np.ndarray:
     """VN positions whose VNs can be "lost" (PD.py:661-666): at least one slot in the counted range
     [ignored_head, num_positions - ignored_tail) and every slot below total_size."""
@@ -256,7 +267,6 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
     fpg = int(frames_per_graph)
     nw = engine.words_for(fpg)
     counted = counted_positions(l, L, num_positions, ignored_head, ignored_tail, bool(is_tail_biting))
-    pos_mask = torch.as_tensor(np.repeat(counted, M))
 
     from . import dist as D
     rank, world = D.world()
@@ -283,24 +293,11 @@ def simulate_sc_ldpc(e, l, r, L, M, is_terminated, is_protograph, is_bounded, is
             fb.generate_erasures(e, seed + 1, first_graph_id=gid0, doping_points=doping_points)
         # non-terminated: the decoder never uses CNs >= total_size (truncated BP, BP_TRAJ.c:944-948 semantics).
         # unbounded: slots below ignored_head_schedule*cns_per_pos are never scanned (PD.py:656), they only decode
-        # when a removal leaves them with one user -- scldpc_bp_set_unscanned_head
-        _lib.check(_lib.lib().scldpc_bp_set_unscanned_head(unscanned))
-        try:
-            res = engine.decode_bp_full(fb, engine.UNLIMITED, is_term=bool(is_terminated) and not is_tail_biting)
-        finally:
-            _lib.lib().scldpc_bp_set_unscanned_head(0)
-        words = res.erased_words                                         # [G][n][W] on the device
-        for g in range(G):
-            tr_g = None
-            for f in np.flatnonzero(res.residual[g] > 0):
-                f = int(f)
-                bits = ((words[g, :, f >> 6] >> (f & 63)) & 1).bool().cpu() & pos_mask
-                lost = torch.nonzero(bits).reshape(-1).numpy()
-                if len(lost) >= 1:
-                    if tr_g is None:
-                        tr_g = fb.vn_cn[g].cpu().numpy()
-                    rec[g * fpg + f] = account_lost(lost, tr_g, M)
-        return rec
+        # when a removal leaves them with one user -- scldpc_bp_full's unscanned_head_cns
+        res = engine.decode_bp_full(fb, engine.UNLIMITED, is_term=bool(is_terminated) and not is_tail_biting,
+                                    unscanned_head_cns=unscanned)
+        # stopping sets of the lost VNs (PD.py:668-691) on the device: one record per frame, one copy per batch
+        return stopping_set_records(fb, res.erased_words, counted)[:, :fpg].reshape(G * fpg, 4).astype(np.int64)
 
     # Frames are decoded in rounds of world_size x graphs_per_batch graphs (rank r takes the r-th batch of the round; graph
     # ids are global), the per-frame records are all-gathered, and every rank then walks the frames in global order with

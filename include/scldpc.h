@@ -46,6 +46,11 @@ extern "C" {
 #define SCLDPC_F_EXP_ALL 8u      /* expurgated statistics over all positions (decodeBP_SW) instead of the first */
 #define SCLDPC_F_STREAM 32u      /* internal: workspace sizing of scldpc_bp_stream */
 #define SCLDPC_F_CHAN_PACKED 16u /* scldpc_decode_host: erased_host is already bit-sliced, uint64 [G][n][n_words] */
+#define SCLDPC_F_MESSAGES 64u    /* pass explicit Lji / Lij messages (the implementation of record) instead of the node-state
+                                    sweeps, which yield the same erased set at every iteration.  Applies
+                                    to scldpc_bp_full without a trajectory, scldpc_bp_window and scldpc_bp_stream; workspace
+                                    sizes depend on it, so pass the same flags to the *_workspace_bytes query and the call  */
+#define SCLDPC_F_NO_WAVE 128u    /* scldpc_bp_full with messages: sweep every position in every iteration (testing)          */
 
 typedef struct {
     int32_t dv, dc;        /* variable / check node degree (Def_dv, Def_dc; BP_FULL.c:22-23)                */
@@ -114,9 +119,12 @@ size_t scldpc_bp_workspace_bytes(const scldpc_dims_t *d, uint32_t flags);
 
 /* Full flooding BP over the BEC -- decodeBP (BP_FULL.c:900-1140, BP_TRAJ.c:901-1151).  max_it <= 0 means
  * unlimited (run until every frame has stalled or finished).  *iters_launched_host (optional) receives the number of
- * flooding iterations launched for the batch. */
+ * flooding iterations launched for the batch.
+ * unscanned_head_cns > 0 -- simulate_sc_ldpc with is_bounded = False (PD.py:604-605,656): slots below
+ * ignored_head_schedule*cns_per_pos are never scanned, they only decode when a removal leaves them with one user.  In BP
+ * terms a CN below unscanned_head_cns that starts with exactly one erased neighbour keeps sending erasures.  0 = off. */
 int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, uint32_t flags,
-                   const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                   int unscanned_head_cns, const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                    int *iters_launched_host, void *stream);
 
 /* Per-position results of the last scldpc_bp_full / scldpc_bp_window call on this workspace, int32 [G][L][64*W] each:
@@ -126,11 +134,14 @@ int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, 
 int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, int32_t *pos_cnt_dev,
                               int32_t *pos_pairs_dev, void *stream);
 
-/* simulate_sc_ldpc with is_bounded = False (PD.py:604-605,656): slots below ignored_head_schedule*cns_per_pos are never
- * scanned, they only decode when a removal leaves them with one user.  In BP terms a CN below n_cns that starts with
- * exactly one erased neighbour keeps sending erasures.  Applies to the following scldpc_bp_full calls of the calling
- * thread; n_cns = 0 switches it off. */
-int scldpc_bp_set_unscanned_head(int n_cns);
+/* Stopping-set bookkeeping of simulate_sc_ldpc (PD.py:659-691) on the residual graph of a decode: per frame the "lost" VNs
+ * (erased VNs of the positions with counted_pos_host[p] != 0; NULL = all) are split into the connected components
+ * extract_stopping_sets would return (PD.py:1077-1095: two lost VNs are connected when they share a CN) and summarised as
+ * out_dev int32 [G][64*W][4] = (num_lost, any component with more than 2 VNs, VNs in such components, VN positions such
+ * components touch) -- num_lost, num_fuckups_truncated, num_lost_exp and len(lost_exp) of PD.py:671-689.
+ * erased_dev: uint64 [G][n][W], e.g. scldpc_bp_out_t.erased_dev of the preceding scldpc_bp_full call. */
+int scldpc_bp_stopping_sets(const scldpc_dims_t *d, const scldpc_batch_t *b, const uint64_t *erased_dev,
+                            const uint8_t *counted_pos_host, int32_t *out_dev, void *stream);
 
 /* Frame streams (lane recycling).  Each graph of the batch decodes frames 0 .. frames_per_graph-1 of its channel
  * stream (the same realisations scldpc_channel_generate produces for those frame ids) with unlimited-iteration full
@@ -140,18 +151,18 @@ int scldpc_bp_set_unscanned_head(int n_cns);
 typedef struct {
     int32_t frames_per_graph;        /* stream length per graph                                                */
     int32_t harvest_every;           /* iterations between harvests (<= 0: adapted to the iterations per frame) */
-    uint32_t flags;                  /* SCLDPC_F_TERMINATED, SCLDPC_F_EXP_ALL                                  */
+    uint32_t flags;                  /* SCLDPC_F_TERMINATED, SCLDPC_F_EXP_ALL, SCLDPC_F_MESSAGES               */
     int32_t n_doped, n_soft;
     const double *eps_host;          /* [G] erasure probability of each graph's channel                        */
     const int32_t *doped_pos_host, *soft_pos_host, *soft_count_host;   /* doping as in scldpc_channel_generate  */
     uint64_t seed, first_graph_id;
     int32_t max_it;                  /* iteration cap per frame, do {} while (iter < MaxNumIt) (BP_FULL.c:1066); <= 0: none.
-                                        Needs the node-state sweeps (the default)                              */
+                                        Needs the node-state sweeps (no SCLDPC_F_MESSAGES)                     */
 } scldpc_stream_cfg_t;
 typedef struct {
     int32_t *iters_dev, *residual_dev, *blocks_err_dev, *erasures_exp_dev, *blocks_err_exp_dev;
 } scldpc_stream_out_t;
-size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d);
+size_t scldpc_bp_stream_workspace_bytes(const scldpc_dims_t *d, uint32_t flags /* SCLDPC_F_MESSAGES or 0 */);
 int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b, const scldpc_stream_cfg_t *cfg,
                      const scldpc_stream_out_t *out, void *workspace_dev, size_t workspace_bytes,
                      long long *iters_launched_host, void *stream);

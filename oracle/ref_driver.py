@@ -123,6 +123,24 @@ class RefLib:
                 CN[c, 1 + CN[c, 0]] = v
                 CN[c, 0] += 1
 
+    def set_graph_fast(self, vn_cn: np.ndarray):
+        """``set_graph`` without the Python loop (full-size graphs): CN rows list their VNs in ascending (v, i) order,
+        which is the order ``generate_code`` appends them in (BP_FULL.c:1702-1716)."""
+        vn_cn = np.asarray(vn_cn, dtype=np.int32).reshape(self.n, self.dv)
+        self.VNdegree[:, 0] = self.dv
+        self.VNdegree[:, 1:] = vn_cn
+        flat = vn_cn.reshape(-1).astype(np.int64)
+        vs = np.repeat(np.arange(self.n, dtype=np.int32), self.dv)
+        order = np.argsort(flat, kind="stable")
+        c_sorted, v_sorted = flat[order], vs[order]
+        deg = np.bincount(flat, minlength=self.nk)
+        if deg.size != self.nk or deg.max() > self.dc:
+            raise ValueError("invalid graph")
+        start = np.cumsum(deg) - deg
+        rank = np.arange(flat.size) - start[c_sorted]
+        self.CNdegree[:, 0] = deg
+        self.CNdegree[c_sorted, 1 + rank] = v_sorted
+
     # ---- channel ----------------------------------------------------------------------------------
     def set_channel(self, erased: np.ndarray):
         self.LLRsChannel[:] = np.asarray(erased).astype(np.int32).reshape(self.n)

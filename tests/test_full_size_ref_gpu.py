@@ -1,0 +1,187 @@
+"""The BENCHMARKED shapes against the UNMODIFIED reference at full size ("next round" item 1).
+
+bench.py decodes G=4 graphs (eps 0.46..0.49) x 16384 frames on 1024 bit-sliced lanes (n_words=16), M=10000, with the
+node-state stream kernels.  This module runs exactly that step (same seed, graph ids and frame ids as the bench's first
+resident batch), pulls the graph and the Philox channel realisation of a sample of frame ids spread over lanes and
+harvests -- including frames that stall at eps=0.49 -- and decodes them with the compiled reference
+(oracle/_ref/ref_traj_4_8_L50_M5000.so, decodeBP of BP_TRAJ.c:901-1151) in a process pool: iterations, residual, blocks,
+expurgated counts.  The same for BASELINE config 3 (capped runs with every trajectory row, capped streams) and config 4
+(decodeBP_SW of BP_SW.c:628-912 at L=100, M=10000, W in {3,10}, 8 iterations per window, 60 for the first), plus the
+derived non-terminated window mode against the oracle port.  All reference jobs share one pool so that the module
+stays inside the driver's pytest budget."""
+import numpy as np
+import pytest
+
+import fl_scaling_sc_ldpc_b200 as eng
+import oracle
+from tests import ref_pool
+
+pytestmark = pytest.mark.gpu
+DV, DC, M = 4, 8, 10000
+SEED = 0x5C1D9C                      # bench.py's default
+EPS = [0.46, 0.47, 0.48, 0.49]
+KEYS = ("iters", "residual", "blocks_err", "erasures_exp", "blocks_err_exp")
+
+
+def _frame_channel(ens, vn_cn_dev, eps, seed, gid, frame):
+    """the channel realisation of frame id `frame` of graph stream `gid` -- what the stream kernels draw in place"""
+    fb = eng.FrameBatch(ens, 1, 4, 2)
+    fb.generate_erasures(eps, seed, first_graph_id=gid, first_frame=frame & ~3)
+    return fb.erasures_host()[0][frame & 3]
+
+
+@pytest.fixture(scope="module")
+def ref_results():
+    """GPU side of every case + ONE pool run of the compiled reference over all of them."""
+    if not (ref_pool.available("traj", DV, DC, 50, M // 2) and ref_pool.available("sw", DV, DC, 100, M // 2)):
+        pytest.skip("oracle/_ref full-size shared objects not built")
+    jobs, meta, gpu = [], [], {}
+
+    # ---- A: the bench step (stream, node-state kernels, unlimited iterations) ----
+    ens = eng.Ensemble(DV, DC, 50, M)
+    fbg = eng.FrameBatch(ens, 4, 1024, 16).generate_graphs(seed=SEED, first_graph_id=0)
+    B = 16384
+    s = eng.decode_bp_stream(fbg, B, EPS, SEED + 1, first_graph_id=0)
+    gpu["stream"] = s
+    vn = fbg.vn_cn.cpu().numpy()
+    picks = []
+    for g in range(3):
+        picks += [(g, f) for f in (5, 1030 + g, 16000 + 7 * g)]
+    fails = np.flatnonzero(s.residual[3] > 0)
+    oks = np.flatnonzero(s.residual[3] == 0)
+    assert len(fails) >= 2 and len(oks) >= 2
+    picks += [(3, int(f)) for f in fails[np.argsort(s.iters[3][fails], kind="stable")[:2]]]
+    picks += [(3, int(f)) for f in oks[np.argsort(s.iters[3][oks], kind="stable")[:2]]]
+    for g, f in picks:
+        ch = _frame_channel(ens, fbg.vn_cn, EPS[g], SEED + 1, g, f)
+        jobs.append(("bp", DV, DC, 50, M // 2, vn[g], ch, dict(max_it=10 ** 9, is_term=1)))
+        meta.append(("stream", g, f))
+
+    # ---- C: capped stream (bp_lim_iter --stream path), cap 175 ----
+    sc = eng.decode_bp_stream(fbg, 2048, EPS, SEED + 1, first_graph_id=0, max_it=175)
+    gpu["capstream"] = sc
+    for g, f in ((1, 3), (2, 1500)):
+        ch = _frame_channel(ens, fbg.vn_cn, EPS[g], SEED + 1, g, f)
+        jobs.append(("bp", DV, DC, 50, M // 2, vn[g], ch, dict(max_it=175, is_term=1)))
+        meta.append(("capstream", g, f))
+
+    # ---- B: capped runs with trajectory rows (config 3), graph of eps = 0.48 ----
+    fbt = eng.FrameBatch(ens, 1, 128, 2)
+    fbt.vn_cn.copy_(fbg.vn_cn[2:3]); fbt._build_tables()
+    fbt.generate_erasures(0.48, SEED + 1, first_graph_id=2, first_frame=0)
+    cht = fbt.erasures_host()[0]
+    for cap, is_term, frames in ((175, 1, (0, 100)), (1000, 1, (64,)), (175, 0, (9,))):
+        r = eng.decode_bp_full(fbt, cap, bool(is_term), trajectory=True, max_rows=cap)
+        gpu[("traj", cap, is_term)] = r
+        for f in frames:
+            jobs.append(("bp", DV, DC, 50, M // 2, vn[2], cht[f], dict(max_it=cap, is_term=is_term, want_rows=True)))
+            meta.append(("traj", cap, is_term, f))
+    del fbt
+
+    # ---- D: window decoder (config 4), L = 100 ----
+    ensw = eng.Ensemble(DV, DC, 100, M)
+    fbw = eng.FrameBatch(ensw, 1, 128, 2).generate_graphs(seed=SEED, first_graph_id=100)
+    vnw = fbw.vn_cn.cpu().numpy()[0]
+    for W, e in ((10, 0.45), (3, 0.36)):
+        fbw.generate_erasures(e, SEED + 2, first_graph_id=100)
+        chw = fbw.erasures_host()[0]
+        gpu[("sw", W)] = eng.decode_bp_window(fbw, W, 8, 60, square=True, is_term=True)
+        gpu[("sw_nt", W)] = (eng.decode_bp_window(fbw, W, 8, 60, square=True, is_term=False), chw.copy())
+        for f in (0, 127):
+            jobs.append(("sw", DV, DC, 100, M // 2, vnw, chw[f], dict(W=W, max_it=8, init_it=60)))
+            meta.append(("sw", W, f))
+    gpu["vnw"] = vnw
+    res = ref_pool.run(jobs)
+    return gpu, list(zip(meta, res))
+
+
+def test_bench_step_matches_compiled_reference(ref_results):
+    gpu, res = ref_results
+    s = gpu["stream"]
+    n = 0
+    for meta, o in res:
+        if meta[0] != "stream":
+            continue
+        _, g, f = meta
+        got = tuple(int(getattr(s, k)[g, f]) for k in KEYS)
+        assert got == tuple(int(o[k]) for k in KEYS), (g, f, got)
+        n += 1
+    assert n == 13
+    # at least two of them are frames that stalled
+    assert sum(1 for meta, o in res if meta[0] == "stream" and o["residual"] > 0) >= 2
+
+
+def test_capped_stream_matches_compiled_reference(ref_results):
+    gpu, res = ref_results
+    s = gpu["capstream"]
+    for meta, o in res:
+        if meta[0] != "capstream":
+            continue
+        _, g, f = meta
+        got = tuple(int(getattr(s, k)[g, f]) for k in KEYS)
+        assert got == tuple(int(o[k]) for k in KEYS), (g, f, got)
+        assert o["iters"] == 175 and o["residual"] > 0          # the cap binds at this size
+
+
+def test_capped_trajectories_match_compiled_reference(ref_results):
+    gpu, res = ref_results
+    n_ens = 50 * M
+    for meta, o in res:
+        if meta[0] != "traj":
+            continue
+        _, cap, is_term, f = meta
+        r = gpu[("traj", cap, is_term)]
+        k = int(r.iters[0, f])
+        assert k == o["iters"] and int(r.residual[0, f]) == o["residual"], meta
+        assert (int(r.blocks_err[0, f]), int(r.erasures_exp[0, f]), int(r.blocks_err_exp[0, f])) == \
+               (o["blocks_err"], o["erasures_exp"], o["blocks_err_exp"]), meta
+        rows = o["rows"]
+        assert (rows[:, 0] == np.arange(k)).all()
+        assert (r.rows[0, f, :k] == rows[:, 1:4]).all(), meta        # deg_1_iter, dVNs, first erased position: every row
+        assert (np.packbits(r.erased()[0, f]) == o["erased"]).all(), meta
+        assert rows[:, 2].sum() == n_ens - o["residual"]
+
+
+def test_window_decoder_matches_compiled_reference(ref_results):
+    gpu, res = ref_results
+    for meta, o in res:
+        if meta[0] != "sw":
+            continue
+        _, W, f = meta
+        r = gpu[("sw", W)]
+        got = (int(r.residual[0, f]), int(r.erasures_p1[0, f]), int(r.blocks_err[0, f]), int(r.erasures_exp[0, f]),
+               int(r.blocks_err_exp[0, f]))
+        assert got == (o["residual"], o["erasures_p1"], o["blocks_err"], o["erasures_exp"], o["blocks_err_exp"]), (meta, got)
+        assert (np.packbits(r.erased()[0, f]) == o["erased"]).all(), meta
+
+
+def test_window_decoder_non_terminated_matches_oracle_port(ref_results):
+    """the derived non-terminated mode (CN window clipped at L*cns_pos) has no compiled counterpart"""
+    gpu, _ = ref_results
+    ensw = eng.Ensemble(DV, DC, 100, M)
+    g = oracle.Graph(gpu["vnw"], 100, M, ensw.cns_pos, DV, DC)
+    for W in (10, 3):
+        r, chw = gpu[("sw_nt", W)]
+        er = r.erased()[0]
+        for f in (1, 126):
+            o = oracle.decode_bp_sw(g, chw[f].astype(np.int32), W, 8, 60, 1, 0)
+            got = (int(r.residual[0, f]), int(r.erasures_p1[0, f]), int(r.blocks_err[0, f]), int(r.iters[0, f]))
+            assert got == (o["residual"], o["erasures_p1"], o["blocks_err"], int(o["win_iters"].sum())), (W, f, got)
+            assert (er[f] == o["erased"]).all()
+
+
+def test_bench_step_sample_matches_oracle_port(ref_results):
+    """a wider sample of the same step against the (much faster) oracle port: 12 frame ids per graph over all harvests"""
+    gpu, _ = ref_results
+    s = gpu["stream"]
+    ens = eng.Ensemble(DV, DC, 50, M)
+    fbg = eng.FrameBatch(ens, 4, 4, 2).generate_graphs(seed=SEED, first_graph_id=0)
+    vn = fbg.vn_cn.cpu().numpy()
+    rng = np.random.default_rng(3)
+    for g in range(4):
+        gg = oracle.Graph(vn[g], 50, M, ens.cns_pos, DV, DC)
+        for f in sorted(rng.choice(16384, 6 if g == 3 else 4, replace=False)):
+            ch = _frame_channel(ens, None, EPS[g], SEED + 1, g, int(f))
+            o = oracle.decode_bp(gg, ch.astype(np.int32), 10 ** 9, 1, max_rows=1)
+            got = tuple(int(getattr(s, k)[g, f]) for k in KEYS)
+            assert got == tuple(int(o[k]) for k in KEYS), (g, f, got)

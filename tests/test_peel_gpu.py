@@ -213,3 +213,31 @@ def test_generated_channel_statistics_and_doping():
     a = eng.FrameBatch(ens, 1, 100).generate_erasures(0.4, 9, first_graph_id=1).erasures_host()
     b = eng.FrameBatch(ens, 2, 100).generate_erasures(0.4, 9, first_graph_id=0).erasures_host()
     assert (a[0] == b[1]).all()                                            # realisations depend on global ids only
+
+
+@pytest.mark.parametrize("dv,dc,L,M", [(4, 8, 12, 40), (3, 6, 9, 30)])
+def test_stopping_set_records_match_host_components(dv, dc, L, M):
+    """scldpc_bp_stopping_sets (local "component has at most two VNs" predicate on the device) against connected components on
+    the host (extract_stopping_sets, PD.py:1077-1095) for arbitrary residual patterns: sparse ones (isolated VNs, pairs,
+    small trees), dense ones, and a mask of counted positions"""
+    ens = eng.Ensemble(dv, dc, L, M)
+    G, F = 2, 150
+    fb = eng.FrameBatch(ens, G, F).generate_graphs(3)
+    rng = np.random.default_rng(11)
+    pat = np.zeros((G, F, ens.n), np.uint8)
+    for g in range(G):
+        for f in range(F):
+            pat[g, f] = rng.random(ens.n) < (0.004, 0.01, 0.03, 0.08, 0.3)[f % 5]
+    fb.set_erasures(pat)
+    vn_cn = fb.vn_cn.cpu().numpy().astype(np.int64)
+    for counted in (np.ones(L, bool), rng.random(L) < 0.7):
+        rec = pdx.stopping_set_records(fb, fb.chan, counted)
+        sizes = set()
+        for g in range(G):
+            for f in range(F):
+                lost = np.flatnonzero(pat[g, f].astype(bool) & np.repeat(counted, M))
+                exp = pdx.account_lost(lost, vn_cn[g], M) if len(lost) else (0, 0, 0, 0)
+                assert tuple(rec[g, f]) == tuple(exp), (g, f, rec[g, f], exp)
+                sizes |= {len(s) for s in pdx.extract_stopping_sets(lost, vn_cn[g])}
+        assert {1, 2, 3} <= sizes          # the interesting component sizes all occurred
+        assert (rec[:, F:] == 0).all()

@@ -45,7 +45,8 @@ def _sync_reference(fb_graphs, ens, B, eps, seed, is_term, doping=(), max_it=0):
 
 
 @pytest.mark.parametrize("L,M,lanes,B,eps", [(10, 50, 128, 700, [0.44, 0.50]), (16, 64, 100, 333, [0.47, 0.41]), (8, 32, 256, 256, [0.5, 0.3]),
-                                               (6, 16, 64, 150, [1.0, 0.0]), (12, 40, 512, 1500, [0.46, 0.52])])
+                                               (6, 16, 64, 150, [1.0, 0.0]), (12, 40, 512, 1500, [0.46, 0.52]),
+                                               (12, 40, 1024, 3000, [0.46, 0.50])])
 def test_stream_equals_synchronous_batches(L, M, lanes, B, eps):
     ens = eng.Ensemble(4, 8, L, M)
     fbg = eng.FrameBatch(ens, 2, lanes).generate_graphs(21, first_graph_id=3)
