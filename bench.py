@@ -221,20 +221,35 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.path = tempfile.mktemp(suffix=".clocks.csv")
         self.proc = None
+        self.t_begin = self.t_end = None
+        # Started BEFORE the warm-up steps (nvidia-smi takes a few hundred ms to initialise NVML, during which host-blocking
+        # CUDA calls stall); mark() brackets the timed region and only its samples are reported.  One sample per second: every NVML query takes a driver lock that host-blocking CUDA calls of the timed region
+        # (the table builder's error-flag read-back) queue behind -- at 10 Hz that cost 50 ms per generated graph
+        period = os.environ.get("SCLDPC_BENCH_CLOCK_MS", "1000")
+        if period == "0":
+            return
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", period,
                                           "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark(self, begin: bool):
+        import datetime
+        if begin:
+            self.t_begin = datetime.datetime.now()
+        else:
+            self.t_end = datetime.datetime.now()
+
     def stop(self) -> dict:
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -250,6 +265,13 @@ class ClockSampler:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
+            if self.t_begin is not None and self.t_end is not None:
+                try:
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f")
+                    if not (self.t_begin <= ts <= self.t_end + datetime.timedelta(seconds=1)):
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(p[1])); mx.append(float(p[2]))
             except ValueError:
@@ -575,6 +597,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
     for i in range(args.warmup):
         step(i, acc=False)
     barrier()
@@ -582,14 +605,15 @@ def run_ours(args):
     # ---- timed region: K steps ------------------------------------------------------------------------------------
     prof = SweepProfile(lib, _lib.check, every=13)       # co-prime with the harvest periods in use
     lib.scldpc_launch_count(1)
-    clocks = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark(True)
     ev0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     ev1.record()
     barrier()
+    clocks.mark(False)
     ms_local = ev0.elapsed_time(ev1)
     launches = lib.scldpc_launch_count(1)
     clk = clocks.stop()

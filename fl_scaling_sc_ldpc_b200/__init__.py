@@ -10,3 +10,4 @@ from .engine import (UNLIMITED, BpResult, Ensemble, FrameBatch, StreamResult, de
 from ._lib import ScldpcError  # noqa: F401
 
 __version__ = "0.1.0"
+from . import engine  # noqa: F401,E402

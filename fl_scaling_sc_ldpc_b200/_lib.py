@@ -25,8 +25,9 @@ F_NO_WAVE = 128
 EXPORTS = [
     "scldpc_last_error", "scldpc_version", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
-    "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_decode_host",
-    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets",
+    "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_bp_window_range", "scldpc_decode_host",
+    "scldpc_graph_generate_at", "scldpc_channel_generate_at",
+    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets", "scldpc_bp_trajectory_moments",
     "scldpc_peel_workspace_bytes", "scldpc_peel_trajectories", "scldpc_peel_variance_accumulate", "scldpc_philox_picks",
     "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end", "scldpc_bp_sweep_stats",
 ]

@@ -87,10 +87,20 @@ def _parser(prog):
     ap.add_argument("--min-frame-err", type=int, default=d["min_frame_err"])
     ap.add_argument("--max-frames", type=int, default=d["max_frames"])
     ap.add_argument("--seed", type=int, default=None)
-    ap.add_argument("--frames-per-graph", type=int, default=128)
-    ap.add_argument("--graphs-per-batch", type=int, default=4)
+    # The reference draws a new code for every frame (BP_FULL.c:2122); bit-slicing needs 64 frames per code.  The default is
+    # that minimum, so a point of max_frames frames averages over max_frames/64 code realisations; more frames per graph
+    # decode faster but correlate the frames of a graph (same estimator, larger variance) -- the value in use is reported on
+    # stderr with the number of graphs behind every point.
+    ap.add_argument("--frames-per-graph", type=int, default=64)
+    ap.add_argument("--graphs-per-batch", type=int, default=16)
     ap.add_argument("--stream", choices=["auto", "on", "off"], default="auto",
                     help="bp_lim_iter: decode each graph's frames as a stream with lane recycling (auto: from 1024 frames per graph)")
+    if prog == "bp_traj":
+        ap.add_argument("--moments-file", default=None,
+                        help="also accumulate the per-iteration moments of the rows on the device (engine.MOMENT_NAMES) and pickle "
+                             "{eps: int64[max_it][8]} here; with --no-text the text rows are not written (large frame counts). "
+                             "Moments cover whole batches: the 'frames' column says how many frames went in")
+        ap.add_argument("--no-text", action="store_true")
     ap.add_argument("--compat-argv", action="store_true", help="read doped positions from argv[4] on like the reference")
     ap.add_argument("--outdir", default=".")
     return ap
@@ -100,13 +110,19 @@ def run(prog: str, argv=None) -> int:
     import os
     import time
     a = _parser(prog).parse_args(argv)
-    raw = list(sys.argv[1:] if argv is None else argv)
     if a.compat_argv:
-        pos = [x for x in raw if not x.startswith("--")]
-        doped = [int(x) for x in pos[3:3 + a.num_doped]]              # argv[4..] of the C program
+        # the C programs read doped_positions[i] = atoi(argv[4 + i]) (BP_FULL.c:2083-2091): argv[4] is MAX_IT, then whatever
+        # follows it.  Taken from the parsed namespace, so option values can never be mistaken for positionals.
+        tail = [a.max_it] + ([a.init_it] if prog == "sw_lim_iter" else []) + ([a.is_term] if prog == "bp_traj" else []) + list(a.doped)
+        if len(tail) < a.num_doped:
+            raise SystemExit(f"{prog}: --compat-argv needs {a.num_doped} values from MAX_IT on")
+        doped = [int(x) for x in tail[: a.num_doped]]
     else:
         doped = list(a.doped)[: a.num_doped]
-    seed = a.seed if a.seed is not None else int(time.time() * 1e6) & 0x7FFFFFFF     # srandom(tv_usec), BP_FULL.c:2059-2062
+    from . import dist as D
+    rank, world = D.init_from_env()
+    # srandom(tv_usec), BP_FULL.c:2059-2062.  Under torchrun every rank must draw from the same stream: rank 0's seed.
+    seed = a.seed if a.seed is not None else D.broadcast_int(int(time.time() * 1e6) & 0x7FFFFFFF)
     vns_pos = a.M * a.dc // a.dv
     ens = engine.Ensemble(a.dv, a.dc, a.L, vns_pos)
     max_it = max(1, a.max_it)                                          # do { } while (iter < MaxNumIt) runs at least once
@@ -117,9 +133,8 @@ def run(prog: str, argv=None) -> int:
         name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_%dinit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, init_it, a.index)
     else:
         name = "SC_LDPC_%d_%d_L%d_M%d_BP_SW%d_%dit_Random_BLER_%d.dat" % (a.dv, a.dc, a.L, a.M, a.W, a.max_it, a.index)
-    from . import dist as D
-    rank, world = D.init_from_env()
     graph_id = 0
+    moments_all = {}
     sw = prog == "sw_lim_iter"
     use_stream = prog == "bp_lim_iter" and (a.stream == "on" or (a.stream == "auto" and fpg >= 1024))
     for sim in range(a.points):
@@ -127,7 +142,9 @@ def run(prog: str, argv=None) -> int:
         c = new_counters()
         f = 0
         traj_f = None
-        if prog == "bp_traj" and rank == 0:
+        mom = None
+        want_mom = prog == "bp_traj" and a.moments_file is not None
+        if prog == "bp_traj" and rank == 0 and not a.no_text:
             tname = "trajectories_%.4f_%s_SC_LDPC_%d_%d_L%d_M%d_BP_Full_%dit_Random_BLER_%d.dat" % (
                 eps, "terminated" if a.is_term else "truncated", a.dv, a.dc, a.L, a.M, a.max_it, a.index)
             traj_f = open(os.path.join(a.outdir, tname), "w")
@@ -162,6 +179,15 @@ def run(prog: str, argv=None) -> int:
             fb.generate_erasures(eps, seed + 1, first_graph_id=gid, doping_points=doped)
             if sw:
                 r = engine.decode_bp_window(fb, a.W, max_it, max(1, init_it), square=True, is_term=True)
+            elif prog == "bp_traj" and want_mom:
+                res_d, erased_d, rows_d, launched = engine.decode_bp_full(fb, max_it, is_term=bool(a.is_term), trajectory=True,
+                                                                          max_rows=max_it, collect=False)
+                mom = engine.trajectory_moments(fb, res_d[0], rows_d, mom)
+                if a.no_text:                                          # nothing but the counters leaves the device
+                    rr = res_d.cpu().numpy()[:, :, :fpg]
+                    r = engine.BpResult(rr[0], rr[1], rr[2], rr[3], rr[4], rr[5], erased_d, None, n_frames=fpg)
+                else:
+                    r = engine._collect(fb, res_d, erased_d, rows_d)
             elif prog == "bp_traj":
                 r = engine.decode_bp_full(fb, max_it, is_term=bool(a.is_term), trajectory=True, max_rows=max_it)
             else:
@@ -169,7 +195,7 @@ def run(prog: str, argv=None) -> int:
             rec = np.stack([r.residual, r.blocks_err, r.erasures_exp, r.blocks_err_exp,
                             r.erasures_p1 if sw else np.zeros_like(r.residual), r.iters], axis=-1).astype(np.int64)
             rec = D.allgather_rows(rec).reshape(-1, 6)                 # [world*G*fpg], global frame order
-            rows = D.allgather_rows(r.rows).reshape((-1,) + r.rows.shape[2:]) if prog == "bp_traj" else None
+            rows = D.allgather_rows(r.rows).reshape((-1,) + r.rows.shape[2:]) if (prog == "bp_traj" and r.rows is not None) else None
             for k in range(len(rec)):
                 if f >= a.max_frames or stop:
                     break
@@ -179,10 +205,23 @@ def run(prog: str, argv=None) -> int:
                 f += 1
                 if c["frame_err"] >= a.min_frame_err:                  # willIstop, BP_FULL.c:440-451
                     stop = True
+        n_graphs_point = (f + fpg - 1) // fpg
         graph_id += (f + G * fpg - 1) // (G * fpg) * G                 # the batches a single process would have drawn
         if traj_f is not None:
             traj_f.close()
+        if want_mom:
+            import pickle
+            m = D.allreduce_counters(mom.cpu().numpy() if mom is not None else np.zeros((max_it, len(engine.MOMENT_NAMES)), np.int64),
+                                     device=D._comm_device() if world > 1 else None)
+            moments_all[float("%.6f" % eps)] = m
+            if rank == 0:
+                with open(os.path.join(a.outdir, a.moments_file), "wb") as mf:
+                    pickle.dump({"names": engine.MOMENT_NAMES, "moments": moments_all}, mf)
         if rank == 0:
+            print("%s: eps=%f frames=%d frames_per_graph=%d graphs=%d frame_err=%d (the reference draws one graph per frame)"
+                  % (prog, eps, f, fpg, n_graphs_point, c["frame_err"]), file=sys.stderr)
+        # BP_TRAJ.c's main_terminated only writes the trajectories file (its risultati call is commented out, :2176)
+        if rank == 0 and prog != "bp_traj":
             with open(os.path.join(a.outdir, name), "w" if sim == 0 else "a") as out:
                 if sim == 0:
                     out.write(HEADER)

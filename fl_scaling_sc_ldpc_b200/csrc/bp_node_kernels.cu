@@ -34,6 +34,18 @@
 
 #include "common.cuh"
 
+// NS_VARIANT: timing experiments only (tools/build_variants.sh); bits: 1 = ld.cg gathers instead of ld.nc.L1::no_allocate
+// (measured: +8 us per launch), 2 = no list stores, 4 = no replay, 8 = no prefix sum.  Variants 2, 4 and 8 decode wrongly by
+// construction (the planes drift apart), so their timings only bound the cost of the part they leave out.
+// 16 = wave instrumentation (tools/wave_skip_measure.py): per iteration, how many (CN position, 128-lane chunk) pairs could a
+// sweep skip because no VN of the dv positions feeding them was resolved in the previous iteration.
+#ifndef NS_VARIANT
+#define NS_VARIANT 0
+#endif
+#ifndef NS_PREFETCH
+#define NS_PREFETCH 1
+#endif
+
 namespace scldpc {
 
 __device__ __forceinline__ uint2 ld_cg_u2(const uint2 *p)
@@ -47,6 +59,12 @@ __device__ __forceinline__ void st_cg_u2(uint2 *p, uint2 v)
     asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// fire-and-forget AND at L2.  atomicAnd() with an unused result compiled to ATOMG (with a response) here, not to RED.
+__device__ __forceinline__ void red_and(unsigned *p, unsigned v)
+{
+    asm volatile("red.global.and.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // replay of one warp's region of the previous launch on plane `w` (32-bit words of graph g)
 __device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int par_prev, unsigned *w, int rid, bool zero_count)
 {
@@ -54,9 +72,15 @@ __device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int p
     int *cntp = p.nl_cnt + (size_t)(g * 2 + par_prev) * RW + rid;
     const int cnt = ld_cg(cntp);
     const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * NS_WCAP;
-    for (int i = threadIdx.x & 31; i < cnt; i += 32) {
-        const uint2 e = ld_cg_u2(reg + i);
-        atomicAnd(w + e.x, ~e.y);
+    // eight independent loads in flight per thread (a region holds ~200 entries): one L2 round trip instead of seven
+    constexpr int U = 8;
+    for (int i0 = threadIdx.x & 31; i0 < cnt; i0 += 32 * U) {
+        uint2 e[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) e[u] = (i0 + 32 * u < cnt) ? ld_cg_u2(reg + i0 + 32 * u) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (e[u].y) red_and(w + e[u].x, ~e[u].y);
     }
     if (zero_count && (threadIdx.x & 31) == 0) *cntp = 0;
 }
@@ -71,7 +95,7 @@ __device__ __forceinline__ void ns_catch_up(const BpParams &p, const u128 *r, u1
         const unsigned ww[4] = {(unsigned)wv.x, (unsigned)(wv.x >> 32), (unsigned)wv.y, (unsigned)(wv.y >> 32)};
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (ww[q] & ~rr[q]) atomicAnd(reinterpret_cast<unsigned *>(w + i) + q, rr[q]);
+            if (ww[q] & ~rr[q]) red_and(reinterpret_cast<unsigned *>(w + i) + q, rr[q]);
     }
 }
 
@@ -108,7 +132,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
 
     // ---- the write plane catches up with the previous iteration ----
     if (ld_cg(p.nl_ovf + g * 2 + (par ^ 1))) ns_catch_up(p, rd, wr);
-    else ns_replay_region(p, g, par ^ 1, wr32, rid, false);
+    else if (!(NS_VARIANT & 4)) ns_replay_region(p, g, par ^ 1, wr32, rid, false);
 
     // ---- check-node sweep ----
     const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
@@ -120,16 +144,23 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     const int stride = gridDim.x * blockDim.x;
     int wcount = 0;                                             // entries this warp has logged (warp-uniform)
     u128 acc_new = zero128();
+    // the index row of the NEXT trip is fetched while this trip's gathers are in flight (the row load was 16 % of the stall
+    // samples as a dependent step in front of the gathers: profiles/r02c)
+    int e[DC];
+    {
+        const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (NS_PREFETCH && lane_work && idx0 < items) load_row<DC>(cn_row + (size_t)(idx0 >> p.chunk_shift) * DC, e);
+    }
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
         const int idx = base + lane;
         u128 res = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
         const int32_t *row = cn_row + (size_t)(idx >> p.chunk_shift) * DC;
         if (lane_work && idx < items) {
-            int e[DC];
-            load_row<DC>(row, e);
+            if (!NS_PREFETCH) load_row<DC>(row, e);
             u128 in[DC];
 #pragma unroll
-            for (int j = 0; j < DC; j++) in[j] = ld_cg128(rdk + (unsigned)e[j]);
+            for (int j = 0; j < DC; j++) in[j] = (NS_VARIANT & 1) ? ld_cg128(rdk + (unsigned)e[j]) : ld_stream(rdk + (unsigned)e[j]);
+            if (NS_PREFETCH && idx + stride < items) load_row<DC>(row + (size_t)(stride >> p.chunk_shift) * DC, e);
             // saturating count of erased neighbours (one / two planes) and, in bit planes b0..b3, the index j of an erased
             // neighbour -- exact where it is needed, i.e. in the frames with exactly one
             u128 one = zero128(), tw = zero128();
@@ -144,18 +175,23 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
             }
             res = one & ~tw;                                    // frames in which exactly one neighbour of c is erased
             if (CAPPED) res &= act;
+#if NS_VARIANT & 16
+            if (nz(res)) reinterpret_cast<int *>(p.pos_er)[((size_t)g * (p.L + DV - 1) + (idx >> p.chunk_shift) / p.cns_pos) * ch + k] = p.iter + 1;
+#endif
         }
         if (__ballot_sync(0xffffffffu, nz(res)) == 0u) continue;
         // slots of this trip's resolutions in the warp's region: exclusive prefix sum of the per-thread counts
         const int c = __popcll(res.x) + __popcll(res.y);
         int incl = c;
+        if (!(NS_VARIANT & 8)) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
         }
         int slot = wcount + incl - c;
-        wcount += __shfl_sync(0xffffffffu, incl, 31);
+        if (!(NS_VARIANT & 8)) wcount += __shfl_sync(0xffffffffu, incl, 31);
         if (c) {
             acc_new |= res;
             const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
@@ -172,8 +208,8 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
                     int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
                     if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
                     const unsigned widx = 4u * ((unsigned)__ldg(row + j) + (unsigned)k) + (unsigned)q;   // L1 hit
-                    atomicAnd(wr32 + widx, ~(1u << b));
-                    if (slot < NS_WCAP) st_cg_u2(reg + slot, make_uint2(widx, 1u << b));
+                    red_and(wr32 + widx, ~(1u << b));
+                    if (!(NS_VARIANT & 2) && slot < NS_WCAP) st_cg_u2(reg + slot, make_uint2(widx, 1u << b));
                     slot++;
                 }
             }
@@ -225,6 +261,25 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
         p.any_new[g * W + w] = 0;
         p.first_new[g * W + w] = 0;
     }
+#if NS_VARIANT & 16
+    {
+        // a CN position must be swept in the next iteration iff a resolution happened within dv-1 positions of it (the resolved
+        // VN sits up to dv-1 positions below the resolving CN and feeds CNs up to dv-1 positions above itself)
+        const int *stamp = reinterpret_cast<const int *>(p.pos_er) + (size_t)g * (p.L + DV - 1) * ch;
+        int needed = 0, total = 0;
+        for (int i = threadIdx.x; i < p.cn_pos_lim * ch; i += blockDim.x) {
+            const int q = i / ch, kk = i % ch;
+            if (!(s_act[2 * kk] | s_act[2 * kk + 1])) continue;
+            total++;
+            bool need = false;
+            for (int d = -(DV - 1); d <= DV - 1; d++)
+                if (q + d >= 0 && q + d < p.L + DV - 1 && stamp[(q + d) * ch + kk] == p.iter + 1) need = true;
+            needed += need;
+        }
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.swept + 2 * g), (unsigned long long)needed);
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.swept + 2 * g + 1), (unsigned long long)total);
+    }
+#endif
     if (threadIdx.x == 0) {
         p.nl_ovf[g * 2 + (par ^ 1)] = 0;                        // consumed by every block of this launch
         p.ticket[g] = 0;

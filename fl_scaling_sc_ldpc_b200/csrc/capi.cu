@@ -34,10 +34,10 @@ int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
 int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge, int32_t *scratch, int *err_dev, int G,
                        int n, int nk, int dv, int dc, cudaStream_t st);
 int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
-                   uint64_t first_graph, int ensemble, cudaStream_t st);
+                   uint64_t first_graph, int ensemble, cudaStream_t st, uint32_t first_position = 0);
 size_t graph_generate_scratch_words(int G, int L, int vns_pos, int cns_pos, int dv, int dc, int ensemble);
 void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
-                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st);
+                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st, uint32_t first_vn = 0);
 void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
 void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
 void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
@@ -45,6 +45,8 @@ int peel_grid(int total_size, long long total_frames);
 size_t peel_state_words(int n_cn_all, int total_size);
 int peel_launch(PeelParams p, int grid, cudaStream_t st);
 int ss_launch(const SsParams &p, cudaStream_t st);
+void traj_moments_launch(const int32_t *rows, const int32_t *iters, int G, int max_rows, int lanes, int n_frames, long long *acc,
+                         cudaStream_t st);
 void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
                           long long *counts, cudaStream_t st);
 }  // namespace scldpc
@@ -292,6 +294,20 @@ extern "C" int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev,
     return 0;
 }
 
+extern "C" int scldpc_graph_generate_at(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
+                                        uint64_t first_graph_id, uint32_t first_position, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!vn_cn_dev || !scratch_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    if (graph_generate(vn_cn_dev, reinterpret_cast<u64 *>(scratch_dev), d->n_graphs, d->L, d->vns_pos, d->cns_pos, d->dv,
+                       d->dc, seed, first_graph_id, 0, static_cast<cudaStream_t>(stream), first_position))
+        return fail(SCLDPC_EINVAL, "cns_pos*dc too large for the key layout");
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting)
 {
     if (check_dims(d)) return 0;
@@ -315,9 +331,29 @@ static int build_known(const scldpc_dims_t *d, const int32_t *doped_pos_host, in
     return 0;
 }
 
+static int channel_generate_impl(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                                 int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
+                                 uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, uint32_t first_vn_id, void *stream);
+
 extern "C" int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
                                        int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
                                        uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, void *stream)
+{
+    return channel_generate_impl(d, chan_dev, eps, doped_pos_host, n_doped, soft_pos_host, soft_count_host, n_soft, seed,
+                                 first_graph_id, first_frame_id, 0, stream);
+}
+
+extern "C" int scldpc_channel_generate_at(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                                          int n_doped, uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id,
+                                          uint32_t first_vn_id, void *stream)
+{
+    return channel_generate_impl(d, chan_dev, eps, doped_pos_host, n_doped, nullptr, nullptr, 0, seed, first_graph_id,
+                                 first_frame_id, first_vn_id, stream);
+}
+
+static int channel_generate_impl(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                                 int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
+                                 uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, uint32_t first_vn_id, void *stream)
 {
     int rc = check_dims(d);
     if (rc) return rc;
@@ -335,7 +371,7 @@ extern "C" int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_de
         CU(cudaStreamSynchronize(st));   // `known` leaves scope below
     }
     channel_generate(reinterpret_cast<u64 *>(chan_dev), d->n_graphs, d->L * d->vns_pos, d->n_words, d->n_frames, d->vns_pos,
-                     known_dev, eps, seed, first_graph_id, first_frame_id, st);
+                     known_dev, eps, seed, first_graph_id, first_frame_id, st, first_vn_id);
     CU(cudaGetLastError());
     if (known_dev) CU(cudaFreeAsync(known_dev, st));
     return 0;
@@ -544,6 +580,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         CU(cudaMemsetAsync(p.noprog, 0, sizeof(u64) * (size_t)p.G * p.W, st));
         CU(cudaMemsetAsync(p.nl_cnt, 0, sizeof(int) * (size_t)p.G * 2 * RW, st));
         CU(cudaMemsetAsync(p.nl_ovf, 0, sizeof(int) * (size_t)p.G * 2, st));
+        CU(cudaMemsetAsync(p.swept, 0, sizeof(long long) * (size_t)p.G * 2, st));        // instrumented builds only
+        CU(cudaMemsetAsync(p.pos_er, 0, sizeof(u64) * (size_t)p.G * d->L * p.W, st));
         bp_launch_node_tables(p, st);
     } else {
         CU(cudaMemsetAsync(p.c2v, 0xFF, sizeof(u128) * (size_t)p.G * p.nk * d->dc * ch, st));
@@ -612,9 +650,39 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     return 0;
 }
 
+// first_window / n_windows: the windows [first_window, first_window + n_windows) of the chain (n_windows < 0: to the end).
+// pending_dev (node-state sweeps only): caller-owned second plane [G][n][W]; with resume != 0 the call continues from the
+// state the caller left in out->erased_dev (what the CNs see) and pending_dev (what each VN has been told so far) instead
+// of initialising both from the channel -- the streaming decoder carries them from one piece of the chain to the next.
+static int bp_window_impl(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                          int first_window, int n_windows, uint64_t *pending_dev, int resume,
+                          const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                          int64_t *edge_updates_host, void *stream);
+
 extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
                                 const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                                 int64_t *edge_updates_host, void *stream)
+{
+    return bp_window_impl(d, b, W, max_it, init_it, flags, 0, -1, nullptr, 0, out, workspace_dev, workspace_bytes, edge_updates_host, stream);
+}
+
+extern "C" int scldpc_bp_window_range(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                                      int first_window, int n_windows, uint64_t *pending_dev, int resume,
+                                      const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                                      int64_t *edge_updates_host, void *stream)
+{
+    if (flags & SCLDPC_F_MESSAGES) return fail(SCLDPC_EINVAL, "window ranges need the node-state sweeps (no SCLDPC_F_MESSAGES)");
+    if (!pending_dev) return fail(SCLDPC_EINVAL, "pending_dev is NULL");
+    if (first_window < 0) return fail(SCLDPC_EINVAL, "first_window must be >= 0");
+    if (d && d->n_frames < 1) return fail(SCLDPC_EINVAL, "n_frames must be >= 1");
+    return bp_window_impl(d, b, W, max_it, init_it, flags, first_window, n_windows, pending_dev, resume, out, workspace_dev,
+                          workspace_bytes, edge_updates_host, stream);
+}
+
+static int bp_window_impl(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                          int first_window, int n_windows, uint64_t *pending_dev, int resume,
+                          const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                          int64_t *edge_updates_host, void *stream)
 {
     if (flags & SCLDPC_F_TRAJECTORY) return fail(SCLDPC_EINVAL, "the window decoder records no trajectory");
     if (W < 1) return fail(SCLDPC_EINVAL, "W must be >= 1");
@@ -632,19 +700,20 @@ extern "C" int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b,
     // form (bpw_*_node_kernel in bp_kernels.cu): same decisions, counters and per-window stopping, about a third of the traffic
     const bool node = !(flags & SCLDPC_F_MESSAGES) && d->n_frames > 0;
     if (node) {
-        p.xb = p.y;                                                // the wave-tracking plane is free in window mode
+        p.xb = pending_dev ? reinterpret_cast<u128 *>(pending_dev) : p.y;   // the wave-tracking plane is free in window mode
         bp_launch_init_ctrl_only(p, d->n_frames, st);
-        bp_launch_window_node_init(p, st);
+        if (!resume) bp_launch_window_node_init(p, st);
     } else {
         bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
         CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
     }
     CU(cudaGetLastError());
+    const int win_end = (n_windows < 0 || first_window + (long long)n_windows > nwin) ? nwin : first_window + n_windows;
     // Opt-in (SCLDPC_PERSISTENT=1): measured on B200 the cooperative kernel is 15-25 % SLOWER than two launches per
     // iteration (W=3: 81 vs 70 ms, W=10: 275 vs 215 ms for 4 graphs x 1024 frames, L=100, M=10000) -- three grid-wide
     // syncs per iteration and 2 instead of 3-4 resident blocks per SM cost more than the launches they replace.
     bool persistent = !node && env_int("SCLDPC_PERSISTENT", 0, 0, 1) != 0;
-    for (int posW = 0; posW < nwin && d->n_frames > 0; posW++) {
+    for (int posW = first_window; posW < win_end && d->n_frames > 0; posW++) {
         long long c0 = (long long)posW * cp, c1 = c0 + (long long)W * cp;
         if (c1 > cn_clip) c1 = cn_clip;
         if (c1 < c0) c1 = c0;
@@ -758,6 +827,20 @@ extern "C" int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(cudaMemcpyAsync(pos_cnt_dev, p.pos_cnt, bytes, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(pos_pairs_dev, p.pos_pairs, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- per-iteration moments of BP trajectories (the notebook's nu_BP / mean dVNs inputs, NB cells 40-42) ----
+extern "C" int scldpc_bp_trajectory_moments(const scldpc_dims_t *d, const int32_t *rows_dev, const int32_t *iters_dev, int max_rows,
+                                            int64_t *acc_dev, void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!rows_dev || !iters_dev || !acc_dev || max_rows < 1) return fail(SCLDPC_EINVAL, "NULL pointer or max_rows < 1");
+    if ((rc = have_device())) return rc;
+    traj_moments_launch(rows_dev, iters_dev, d->n_graphs, max_rows, 64 * d->n_words, d->n_frames, reinterpret_cast<long long *>(acc_dev),
+                        static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
     return 0;
 }
 

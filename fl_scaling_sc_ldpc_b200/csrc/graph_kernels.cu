@@ -66,11 +66,13 @@ int graph_build_tables(const int32_t *vn_cn, int32_t *vn_slot, int32_t *cn_edge,
 #define KEY_IDX_BITS 20          // low bits carry the socket index (S <= 2^20)
 
 // keys[seg][s] = (random << KEY_IDX_BITS) | s for s < S, all-ones padding up to Spad.  seg = g*npos + pos.
-__global__ void graph_keys_kernel(u64 *keys, int S, int Spad, int npos, uint64_t seed, uint64_t first_graph)
+// pos0: absolute index of the chain's first position (streams decoded in consecutive, overlapping pieces draw the same
+// permutation for the same absolute CN position)
+__global__ void graph_keys_kernel(u64 *keys, int S, int Spad, int npos, uint64_t seed, uint64_t first_graph, uint32_t pos0)
 {
     const int seg = blockIdx.x;                       // segments on grid.x: G * npos can exceed the 65535 limit of grid.y
     const uint64_t gid = first_graph + (uint64_t)(seg / npos);
-    const uint32_t pos = (uint32_t)(seg % npos);
+    const uint32_t pos = pos0 + (uint32_t)(seg % npos);
     for (int q = blockIdx.y * blockDim.x + threadIdx.x; q < Spad / 2; q += gridDim.y * blockDim.x) {
         uint32_t r[4];
         // counter = (socket pair, position, graph id); key = seed ^ domain tag "graph"
@@ -169,8 +171,9 @@ __global__ void graph_from_keys_proto_kernel(const u64 *keys, int32_t *vn_cn, in
 
 // ensemble: 0 = semi-structured (generate_code / SC.gen_slots), 1 = its tail-biting variant, 2 = protograph-based
 int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns_pos, int dv, int dc, uint64_t seed,
-                   uint64_t first_graph, int ensemble, cudaStream_t st)
+                   uint64_t first_graph, int ensemble, cudaStream_t st, uint32_t first_position)
 {
+    if (first_position && ensemble != 0) return -1;
     const bool proto = ensemble == 2;
     const int tail_biting = ensemble == 1;
     if (proto && (vns_pos % cns_pos)) return -1;
@@ -183,7 +186,7 @@ int graph_generate(int32_t *vn_cn, u64 *keys, int G, int L, int vns_pos, int cns
     const int segs = G * npos;
     unsigned bx = (unsigned)((Spad / 2 + 255) / 256);
     if (bx > 64) bx = 64;
-    graph_keys_kernel<<<dim3(segs, bx), 256, 0, st>>>(keys, S, Spad, npos, seed, first_graph);
+    graph_keys_kernel<<<dim3(segs, bx), 256, 0, st>>>(keys, S, Spad, npos, seed, first_graph, first_position);
     const int tile = Spad < SORT_TILE ? Spad : SORT_TILE;
     int lt = 0;
     while ((1 << lt) < tile) lt++;
@@ -216,8 +219,9 @@ size_t graph_generate_scratch_words(int G, int L, int vns_pos, int cns_pos, int 
 // ------------------------------------------------------------------------------------------------------------
 // chan[g][v][w] bit b = 1 (erased) iff channel_draw(seed; graph, frame first_frame+64w+b, v) < eps * 2^32, unless v is among the first
 // known[pos] VNs of its position (doping).  One Philox call yields the draws of 4 consecutive frames.
+// v0: absolute index of the chain's first VN (stream pieces, see graph_keys_kernel)
 __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, int vns_pos, const int32_t *known,
-                                        u64 thr, uint64_t seed, uint64_t first_graph, uint32_t first_frame)
+                                        u64 thr, uint64_t seed, uint64_t first_graph, uint32_t first_frame, uint32_t v0)
 {
     const int g = blockIdx.y;
     const uint64_t gid = first_graph + (uint64_t)g;
@@ -231,7 +235,7 @@ __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, i
             for (int q = 0; q < 16; q++) {
                 uint32_t r[4];
                 // frame ids of this Philox call: first_frame + 64w + 4q + {0,1,2,3}; first_frame is a multiple of 4
-                philox4x32_10((uint32_t)v, (first_frame >> 2) + (uint32_t)(w * 16 + q), (uint32_t)gid, (uint32_t)(gid >> 32),
+                philox4x32_10(v0 + (uint32_t)v, (first_frame >> 2) + (uint32_t)(w * 16 + q), (uint32_t)gid, (uint32_t)(gid >> 32),
                               (uint32_t)seed ^ 0x6368616Eu, (uint32_t)(seed >> 32), r);
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
@@ -245,7 +249,7 @@ __global__ void channel_generate_kernel(u64 *chan, int n, int W, int n_frames, i
 }
 
 void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos, const int32_t *known_dev, double eps,
-                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st)
+                      uint64_t seed, uint64_t first_graph, uint32_t first_frame, cudaStream_t st, uint32_t first_vn)
 {
     u64 thr;
     if (eps <= 0.0) thr = 0;
@@ -253,7 +257,7 @@ void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos,
     else thr = (u64)(eps * 4294967296.0);
     const long long items = (long long)n * W;
     unsigned bx = (unsigned)((items + 255) / 256 < 2368 ? (items + 255) / 256 : 2368);
-    channel_generate_kernel<<<dim3(bx, G), 256, 0, st>>>(chan, n, W, n_frames, vns_pos, known_dev, thr, seed, first_graph, first_frame);
+    channel_generate_kernel<<<dim3(bx, G), 256, 0, st>>>(chan, n, W, n_frames, vns_pos, known_dev, thr, seed, first_graph, first_frame, first_vn);
 }
 
 // bytes [G][F][n] (1 = erased) -> bit-sliced words [G][n][W]

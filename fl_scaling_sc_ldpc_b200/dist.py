@@ -60,6 +60,15 @@ def allreduce_counters(values, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+def broadcast_int(value: int) -> int:
+    """rank 0's value on every rank (e.g. a time-derived default seed: every rank must draw from the same stream)"""
+    if world()[1] == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_comm_device())
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
 def allreduce_max(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64)
     if device is not None:

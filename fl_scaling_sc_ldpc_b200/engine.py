@@ -108,10 +108,23 @@ class FrameBatch:
         self._build_tables()
         return self
 
-    def generate_graphs(self, seed: int, first_graph_id: int = 0, tail_biting: bool = False, protograph: bool = False) -> "FrameBatch":
+    def generate_graphs(self, seed: int, first_graph_id: int = 0, tail_biting: bool = False, protograph: bool = False,
+                        first_position: int = 0) -> "FrameBatch":
         """Draw graphs on the device: the semi-structured ensemble (``generate_code`` BP_FULL.c:1656 / ``SC.gen_slots``
-        SC.py:53), its tail-biting variant, or the protograph-based ensemble (``sc_ldpc_protograph.py``)."""
+        SC.py:53), its tail-biting variant, or the protograph-based ensemble (``sc_ldpc_protograph.py``).
+        ``first_position`` > 0: the batch is a piece of a longer chain starting at that absolute position (streams)."""
         L = _lib.lib()
+        if first_position:
+            if tail_biting or protograph:
+                raise ValueError("chain pieces exist for the semi-structured ensemble only")
+            nbytes = L.scldpc_graph_generate_scratch_bytes(ctypes.byref(self.dims), 0)
+            if self._keys is None or self._keys.numel() * 8 < nbytes:
+                self._keys = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=self.device)
+            _lib.check(L.scldpc_graph_generate_at(ctypes.byref(self.dims), ctypes.c_void_p(self.vn_cn.data_ptr()),
+                                                  ctypes.c_void_p(self._keys.data_ptr()), ctypes.c_uint64(seed),
+                                                  ctypes.c_uint64(first_graph_id), ctypes.c_uint32(first_position), _stream()))
+            self._build_tables()
+            return self
         ensemble = 2 if protograph else int(bool(tail_biting))
         tail_biting = ensemble
         nbytes = L.scldpc_graph_generate_scratch_bytes(ctypes.byref(self.dims), int(tail_biting))
@@ -135,11 +148,22 @@ class FrameBatch:
                                                        ctypes.c_void_p(self.chan.data_ptr()), _stream()))
         return self
 
-    def generate_erasures(self, eps, seed: int, first_graph_id: int = 0, doping_points=(), first_frame: int = 0) -> "FrameBatch":
+    def generate_erasures(self, eps, seed: int, first_graph_id: int = 0, doping_points=(), first_frame: int = 0,
+                          first_vn: int = 0) -> "FrameBatch":
         """BEC(eps) realisations on the device; ``eps`` is a float or one value per graph of the batch.
         ``doping_points``: list of positions (hard doping) or dict {position: alpha} (soft doping: the first
         int(alpha*M) VNs are known, PD.py:175-183).  Lane f holds frame ``first_frame + f`` of the graph's channel
-        stream (``first_frame`` a multiple of 4)."""
+        stream (``first_frame`` a multiple of 4).  ``first_vn`` > 0: the batch is a piece of a longer chain whose first VN
+        has that absolute index (hard doping only; positions are local to the piece)."""
+        if first_vn:
+            if isinstance(doping_points, dict) or np.ndim(eps) != 0:
+                raise ValueError("chain pieces take one eps and hard doping only")
+            hard = [int(p) for p in doping_points]
+            a = (ctypes.c_int32 * max(1, len(hard)))(*hard)
+            _lib.check(_lib.lib().scldpc_channel_generate_at(
+                ctypes.byref(self.dims), ctypes.c_void_p(self.chan.data_ptr()), ctypes.c_double(float(eps)), a, len(hard),
+                ctypes.c_uint64(seed), ctypes.c_uint64(first_graph_id), ctypes.c_uint32(first_frame), ctypes.c_uint32(first_vn), _stream()))
+            return self
         hard, soft_p, soft_c = [], [], []
         if isinstance(doping_points, dict):
             for pos, alpha in doping_points.items():
@@ -255,6 +279,23 @@ def decode_bp_full(fb: FrameBatch, max_it: int = UNLIMITED, is_term: bool = True
     return r
 
 
+MOMENT_NAMES = ("frames", "frames_dvn_nonzero", "sum_dvn", "sum_dvn2", "sum_deg1", "sum_deg1_2", "sum_first_pos", "sum_dvn_deg1")
+
+
+def trajectory_moments(fb: FrameBatch, iters_dev: torch.Tensor, rows_dev: torch.Tensor, acc: torch.Tensor | None = None) -> torch.Tensor:
+    """Adds the per-iteration moments of a trajectory decode (``decode_bp_full(..., trajectory=True, collect=False)``:
+    ``iters_dev = res[0]``, ``rows_dev = rows``) to ``acc`` int64 [max_rows][8] on the device (``MOMENT_NAMES``) --
+    ``scldpc_bp_trajectory_moments``; what the notebook computes from bp_traj's text rows (NB cells 40-42), without the
+    rows ever leaving the device."""
+    max_rows = int(rows_dev.shape[1])
+    if acc is None:
+        acc = torch.zeros((max_rows, len(MOMENT_NAMES)), dtype=torch.int64, device=fb.device)
+    assert acc.shape == (max_rows, len(MOMENT_NAMES)) and acc.is_contiguous()
+    _lib.check(_lib.lib().scldpc_bp_trajectory_moments(ctypes.byref(fb.dims), ctypes.c_void_p(rows_dev.data_ptr()),
+                                                      ctypes.c_void_p(iters_dev.data_ptr()), max_rows, ctypes.c_void_p(acc.data_ptr()), _stream()))
+    return acc
+
+
 def position_counts(fb: FrameBatch, flags: int):
     """Per-position erased-VN counts and accepted size-two stopping sets of the last decode on ``fb``:
     two int32 arrays [n_graphs][L][n_frames]."""
@@ -279,6 +320,25 @@ def decode_bp_window(fb: FrameBatch, W: int, max_it: int, init_it: int = 0, squa
     if not collect:
         return res, erased, rows, 0
     return _collect(fb, res, erased, rows, edge_updates=work.value)
+
+
+def decode_bp_window_range(fb: FrameBatch, W: int, max_it: int, first_window: int, n_windows: int, erased: torch.Tensor,
+                           pending: torch.Tensor, resume: bool, init_it: int = 0, square: bool = False, is_term: bool = True):
+    """Windows [first_window, first_window + n_windows) of ``decode_bp_window`` with the decoder state owned by the caller
+    (``scldpc_bp_window_range``): ``erased`` (what the CNs see; ends as the decisions) and ``pending`` (what every VN has been
+    told so far), int64 [G][n][W] each.  ``resume=False`` initialises them from ``fb.chan``.  Returns the per-frame result
+    tensor int32 [6][G][lanes] (device); per-position counts through ``position_counts``."""
+    flags = (F_TERMINATED if is_term else 0) | (F_SQUARE if square else 0) | F_EXP_ALL
+    G, lanes = fb.n_graphs, 64 * fb.n_words
+    res = torch.zeros((6, G, lanes), dtype=torch.int32, device=fb.device)
+    assert erased.shape == pending.shape == (G, fb.ens.n, fb.n_words) and erased.is_contiguous() and pending.is_contiguous()
+    out = _lib.BpOut(res[0].data_ptr(), res[1].data_ptr(), res[2].data_ptr(), res[3].data_ptr(), res[4].data_ptr(),
+                     res[5].data_ptr(), erased.data_ptr(), None, 0)
+    ws = fb.workspace(flags)
+    _lib.check(_lib.lib().scldpc_bp_window_range(ctypes.byref(fb.dims), ctypes.byref(fb.cbatch), int(W), int(max_it), int(init_it), flags,
+                                                 int(first_window), int(n_windows), ctypes.c_void_p(pending.data_ptr()), int(bool(resume)),
+                                                 ctypes.byref(out), ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), None, _stream()))
+    return res
 
 
 @dataclass

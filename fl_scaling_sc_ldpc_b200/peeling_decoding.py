@@ -125,6 +125,8 @@ def simulate_peeling_decoder_ldpc(e, l_deg, r_deg, L, M, is_terminated, is_proto
     if world > 1 and not _local:
         # every rank peels a contiguous range of the frames (frame ids are global) and the results are all-gathered
         q = (num_repeats + world - 1) // world
+        fpg_ = max(1, int(frames_per_graph))
+        q = (q + fpg_ - 1) // fpg_ * fpg_                              # whole graphs per rank: frame F is (graph F // fpg, lane F % fpg)
         lo, hi = min(rank * q, num_repeats), min((rank + 1) * q, num_repeats)
         cols = _peel_geometry(e, l_deg, r_deg, L, M, is_terminated)[3] + 1
         if hi > lo:

@@ -102,6 +102,12 @@ int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_batch_t *b, i
 int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
                           uint64_t first_graph_id, int tail_biting, void *stream);
 size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biting);
+/* Semi-structured ensemble for a PIECE of a longer chain: local position j of the piece is absolute position
+ * first_position + j, and CN position p draws the same socket permutation whatever piece it is generated in -- the
+ * streaming decoder (main_streaming / generate_code_pos, BP_FULL.c:1820-1856, :2003-2012) walks an unbounded chain in
+ * overlapping pieces.  Scratch as for scldpc_graph_generate with ensemble 0. */
+int scldpc_graph_generate_at(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
+                             uint64_t first_graph_id, uint32_t first_position, void *stream);
 
 /* ---- channel ------------------------------------------------------------------------------------------ */
 /* BEC realisations, bit-sliced (channel_doped, BP_FULL.c:1547-1574; PD.py:154, :174-192).  Lane f of graph g holds
@@ -110,6 +116,12 @@ size_t scldpc_graph_generate_scratch_bytes(const scldpc_dims_t *d, int tail_biti
 int scldpc_channel_generate(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
                             int n_doped, const int32_t *soft_pos_host, const int32_t *soft_count_host, int n_soft,
                             uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id, void *stream);
+
+/* Channel realisations for a piece of a longer chain (generate_channel_doped_circular, BP_FULL.c:1621-1654): local VN v is
+ * VN first_vn_id + v of the stream, so overlapping pieces see the same erasures.  Hard doping only (local positions). */
+int scldpc_channel_generate_at(const scldpc_dims_t *d, uint64_t *chan_dev, double eps, const int32_t *doped_pos_host,
+                               int n_doped, uint64_t seed, uint64_t first_graph_id, uint32_t first_frame_id,
+                               uint32_t first_vn_id, void *stream);
 
 /* Packs byte-per-VN erasure patterns (host, [G][n_frames][n], 1 = erased) into chan_dev. */
 int scldpc_channel_pack_host(const scldpc_dims_t *d, const uint8_t *erased_host, uint64_t *chan_dev, void *stream);
@@ -133,6 +145,14 @@ int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, int max_it, 
  * accumulate position by position (BP_FULL.c:1483-1497, :2015-2031). */
 int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags, void *workspace_dev, int32_t *pos_cnt_dev,
                               int32_t *pos_pairs_dev, void *stream);
+
+/* Per-iteration moments of the trajectory rows of a scldpc_bp_full call with SCLDPC_F_TRAJECTORY, accumulated (+=) into
+ * acc_dev int64 [max_rows][8]: per iteration t = (frames that executed t, frames with dVNs != 0, sum dVNs, sum dVNs^2,
+ * sum deg_1_iter, sum deg_1_iter^2, sum first erased position, sum dVNs*deg_1_iter).  These are what the notebook derives
+ * from bp_traj's text rows (BP_TRAJ.c:988,1051; NB cells 40-42: mean dVNs over non-zero entries, variance around the
+ * mean-evolution curve with finished frames zero-padded) -- exact integers, additive over batches and ranks. */
+int scldpc_bp_trajectory_moments(const scldpc_dims_t *d, const int32_t *rows_dev, const int32_t *iters_dev, int max_rows,
+                                 int64_t *acc_dev, void *stream);
 
 /* Stopping-set bookkeeping of simulate_sc_ldpc (PD.py:659-691) on the residual graph of a decode: per frame the "lost" VNs
  * (erased VNs of the positions with counted_pos_host[p] != 0; NULL = all) are split into the connected components
@@ -179,6 +199,17 @@ int scldpc_stream_host(const scldpc_dims_t *d, const int32_t *vn_cn_host, const 
 int scldpc_bp_window(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
                      const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
                      int64_t *edge_updates_host, void *stream);
+
+/* A range of windows of scldpc_bp_window, with the decoder state owned by the caller: windows [first_window, first_window +
+ * n_windows) (n_windows < 0: to the end); pending_dev uint64 [G][n][W] is the second state plane of the node-state sweeps
+ * (what every VN has been told so far; out->erased_dev holds what the CNs see).  resume == 0 initialises both planes from
+ * the channel; resume != 0 continues from what the caller put there -- decodeBP_SW_circular (BP_FULL.c:1403-1500) decodes an
+ * unbounded chain position by position, here piece by piece with the state of the overlap carried over.  Node-state sweeps
+ * only.  Per-frame outputs and scldpc_bp_position_counts cover the whole piece; positions not yet decided are not final. */
+int scldpc_bp_window_range(const scldpc_dims_t *d, const scldpc_batch_t *b, int W, int max_it, int init_it, uint32_t flags,
+                           int first_window, int n_windows, uint64_t *pending_dev, int resume,
+                           const scldpc_bp_out_t *out, void *workspace_dev, size_t workspace_bytes,
+                           int64_t *edge_updates_host, void *stream);
 
 /* Reference-facing convenience entry point with HOST buffers (what a maintainer would call in place of
  * generate_code + channel_doped + decodeBP, BP_FULL.c:2122-2133): uploads vn_cn_host [G][n][dv] and erased_host

@@ -18,6 +18,8 @@ CASES = [  # name, dv, dc, ring L, Def_M, W, eps, doped positions, decode steps,
     ("c1", 4, 8, 24, 16, 8, 0.55, [5, 7, 9], 90, 12),
     ("c2", 3, 6, 16, 12, 6, 0.40, [6], 60, 13),
     ("c3", 4, 8, 24, 16, 10, 0.47, [], 50, 14),
+    # long undoped run: windows fail and the erasures they leave behind keep propagating (several pieces of ChainPieces)
+    ("c4", 4, 8, 24, 16, 8, 0.50, [], 220, 15),
 ]
 
 

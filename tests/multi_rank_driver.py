@@ -25,9 +25,13 @@ streaming.main_streaming(["4", "5", "0", "--L", "16", "--M", "16", "--eps-ini", 
                           "--max-blocks-err", "30", "--max-blocks", "20000", "--outdir", out])
 # 3. peeling trajectories + the variance driver
 _, r1, plrs = pdx.simulate_peeling_decoder_ldpc(0.45, 4, 8, 12, 64, False, False, 37, seed=11)
+# frames_per_graph > 1: every rank must start on a graph boundary (frame F is graph F // fpg, lane F % fpg)
+_, r1g, plrsg = pdx.simulate_peeling_decoder_ldpc(0.45, 4, 8, 12, 64, False, False, 37, seed=11, frames_per_graph=8)
 if rank == 0:
     with open(os.path.join(out, "peel.pkl"), "wb") as f:
         pickle.dump((np.asarray(r1), np.asarray(plrs)), f)
+    with open(os.path.join(out, "peel_fpg8.pkl"), "wb") as f:
+        pickle.dump((np.asarray(r1g), np.asarray(plrsg)), f)
     with open(os.path.join(out, "theory.in"), "wb") as f:
         pickle.dump((np.asarray(r1, np.float64).mean(axis=0),), f)
 if world > 1:

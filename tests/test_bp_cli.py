@@ -46,6 +46,8 @@ def test_cli_end_to_end(tmp_path):
     t = (tmp_path / "trajectories_0.4400_truncated_SC_LDPC_4_8_L10_M25_BP_Full_60it_Random_BLER_1.dat").read_text()
     frames = t.strip("\n").split("\n\n")
     assert 1 <= len(frames) <= 40
+    # BP_TRAJ.c's main_terminated writes the trajectories file only (risultati is commented out, :2176)
+    assert not [f for f in os.listdir(tmp_path) if "_60it_" in f and not f.startswith("trajectories_")]
     first = [ln.split("\t") for ln in frames[0].split("\n")]
     assert [int(r[0]) for r in first] == list(range(len(first))) and all(len(r) == 4 for r in first)
     assert int(first[0][2]) > 0 and int(first[-1][3]) <= 10
@@ -67,3 +69,12 @@ def test_bp_lim_iter_stream_path_writes_the_same_file(tmp_path):
     assert files["on"] == files["off"]
     rows = files["on"][1].splitlines()
     assert len(rows) == 3 and float(rows[1].split()[2]) > 0          # header + 2 points, some frame errors at eps = 0.48
+
+
+def test_compat_argv_reads_doped_positions_from_max_it_on():
+    """--compat-argv: doped_positions[i] = atoi(argv[4+i]) (BP_FULL.c:2083-2091) -- MAX_IT first, then what follows; option
+    values in between must not shift it"""
+    from fl_scaling_sc_ldpc_b200 import bp_cli as b
+    a = b._parser("bp_lim_iter").parse_args(["--M", "100", "0", "50", "2", "20", "7", "--compat-argv"])
+    tail = [a.max_it] + list(a.doped)
+    assert tail[: a.num_doped] == [20, 7]

@@ -183,3 +183,24 @@ def test_malformed_graph_is_rejected():
     bad = np.zeros((1, ens.n, 4), np.int32)          # every edge on CN 0
     with pytest.raises(eng.ScldpcError):
         fb.set_graphs(bad)
+
+
+def test_trajectory_moments_on_the_device():
+    """scldpc_bp_trajectory_moments: per-iteration counts / sums of the rows, accumulated over two batches on the device,
+    against NumPy on the collected rows (the notebook's reductions of bp_traj files, NB cells 40-42)"""
+    ens = eng.Ensemble(4, 8, 12, 48)
+    cap = 40
+    acc, ref = None, np.zeros((cap, 8), np.int64)
+    for b, nf in enumerate((100, 128)):
+        fb = eng.FrameBatch(ens, 2, nf).generate_graphs(5, first_graph_id=2 * b).generate_erasures([0.44, 0.49], 6, first_graph_id=2 * b)
+        res, erased, rows, _ = eng.decode_bp_full(fb, cap, True, trajectory=True, max_rows=cap, collect=False)
+        acc = eng.engine.trajectory_moments(fb, res[0], rows, acc)
+        r = eng.engine._collect(fb, res, erased, rows)
+        for t in range(cap):
+            live = r.iters > t
+            d1, dv, fp = (r.rows[:, :, t, k].astype(np.int64) for k in range(3))
+            ref[t] += [live.sum(), (live & (dv != 0)).sum(), dv[live].sum(), (dv[live] ** 2).sum(), d1[live].sum(), (d1[live] ** 2).sum(),
+                       fp[live].sum(), (dv[live] * d1[live]).sum()]
+            assert not r.rows[:, :, t][~live].any()                   # rows of stopped frames are the zero padding
+    assert (acc.cpu().numpy() == ref).all()
+    assert ref[0, 0] == 2 * 228 and ref[-1, 0] < ref[0, 0]

@@ -84,3 +84,22 @@ def test_num_pd_steps_float_truncation():
     assert pdx._peel_geometry(0.48, 4, 8, 50, 1000, False)[3] == 28999
     assert pdx._peel_geometry(0.48, 4, 8, 50, 1000, True)[3] == 30739
     assert pdx._peel_geometry(0.48, 4, 8, 50, 10000, False)[3] == 290000
+
+
+def test_variance_golden_is_what_the_reference_computes():
+    """tests/golden/var_golden.npz against the imported reference (this container only; the GPU test compares the kernel
+    with the stored arrays)"""
+    from oracle import peeling_ref as pr
+    if not pr.available():
+        pytest.skip("reference not present")
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_var_golden", os.path.join(here, "golden", "make_var_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(here, "golden", "var_golden.npz"))
+    r1, theory, M = mod.inputs()
+    assert np.array_equal(r1.astype(np.int32), z["r1"]) and np.array_equal(theory, z["theory"])
+    for k, (ssq, cnt) in enumerate(mod.reference_chunks(pr.load(), r1, theory, M)):
+        assert np.array_equal(ssq, z[f"ssq{k}"]) and np.array_equal(cnt, z[f"cnt{k}"])

@@ -241,3 +241,15 @@ def test_stopping_set_records_match_host_components(dv, dc, L, M):
                 sizes |= {len(s) for s in pdx.extract_stopping_sets(lost, vn_cn[g])}
         assert {1, 2, 3} <= sizes          # the interesting component sizes all occurred
         assert (rec[:, F:] == 0).all()
+
+
+def test_variance_accumulation_matches_the_reference_function():
+    """P5 pinned to the reference itself: tests/golden/var_golden.npz holds what the imported est_scaling_params.calc_nu_chunk
+    returned for two chunks (tests/golden/make_var_golden.py); the fused kernel must reproduce both chunks bit for bit"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "var_golden.npz"))
+    r1, theory, M = z["r1"], z["theory"], int(z["M"])
+    for k, (lo, hi) in enumerate(((0, 10), (10, r1.shape[0]))):
+        ssq, cnt = pdx.calc_nu_chunk_device([torch.as_tensor(r1[lo:hi]).cuda()], theory, M)
+        assert np.array_equal(cnt, z[f"cnt{k}"]), k
+        assert np.array_equal(ssq, z[f"ssq{k}"]), k                  # float64, same summation order: exact

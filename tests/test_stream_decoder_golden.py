@@ -10,7 +10,7 @@ import pytest
 import oracle
 
 Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stream_golden.npz"))
-CASES = ["c0", "c1", "c2", "c3"]
+CASES = ["c0", "c1", "c2", "c3", "c4"]
 
 
 def case(name):
