@@ -23,11 +23,11 @@ F_MESSAGES = 64
 F_NO_WAVE = 128
 
 EXPORTS = [
-    "scldpc_last_error", "scldpc_version", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
+    "scldpc_last_error", "scldpc_version", "scldpc_build_info", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
     "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_bp_window_range", "scldpc_decode_host",
     "scldpc_graph_generate_at", "scldpc_channel_generate_at",
-    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets", "scldpc_bp_trajectory_moments",
+    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets", "scldpc_bp_trajectory_moments", "scldpc_pairwise_moments_accumulate",
     "scldpc_peel_workspace_bytes", "scldpc_peel_trajectories", "scldpc_peel_variance_accumulate", "scldpc_philox_picks",
     "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end", "scldpc_bp_sweep_stats",
 ]
@@ -67,11 +67,28 @@ class StreamOut(ctypes.Structure):
 _lib = None
 
 
+def source_hash() -> str:
+    """hash of the sources on disk, as the Makefile computes it (``scldpc_build_info`` carries the one the .so was built from)"""
+    return subprocess.run(["make", "-s", "-C", CSRC, "print-hash"], check=True, capture_output=True, text=True).stdout.strip()
+
+
 def build(force: bool = False) -> str:
-    """Compile libscldpc.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile libscldpc.so for sm_100a (nvcc cross-compiles without a GPU).  ``force``: ``make clean`` first, so every
+    object is compiled from the sources on disk; a record of the build goes to ``build_record.json`` next to the library."""
+    import json
+    import time
+    t0 = time.time()
     if force:
         subprocess.run(["make", "-s", "-C", CSRC, "clean"], check=True)
-    subprocess.run(["make", "-s", "-C", CSRC, "-j4"], check=True)
+    subprocess.run(["make", "-s", "-C", CSRC, "-j8"], check=True)
+    objs = sorted(f for f in os.listdir(CSRC) if f.endswith(".o"))
+    rec = {"mode": "clean" if force else "incremental", "seconds": round(time.time() - t0, 1), "source_hash": source_hash(),
+           "library": os.path.basename(LIB_PATH), "library_bytes": os.path.getsize(LIB_PATH),
+           "objects": {o: {"bytes": os.path.getsize(os.path.join(CSRC, o)), "mtime": os.path.getmtime(os.path.join(CSRC, o))} for o in objs},
+           "nvcc": subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1],
+           "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
+    with open(os.path.join(HERE, "build_record.json"), "w") as f:
+        json.dump(rec, f, indent=1)
     return LIB_PATH
 
 
@@ -83,6 +100,7 @@ def lib() -> ctypes.CDLL:
                               f"or `make -C {CSRC}`; there is no CPU fallback")
         L = ctypes.CDLL(LIB_PATH)
         L.scldpc_last_error.restype = ctypes.c_char_p
+        L.scldpc_build_info.restype = ctypes.c_char_p
         L.scldpc_bp_workspace_bytes.restype = ctypes.c_size_t
         L.scldpc_bp_stream_workspace_bytes.restype = ctypes.c_size_t
         L.scldpc_graph_generate_scratch_bytes.restype = ctypes.c_size_t

@@ -45,6 +45,7 @@ int peel_grid(int total_size, long long total_frames);
 size_t peel_state_words(int n_cn_all, int total_size);
 int peel_launch(PeelParams p, int grid, cudaStream_t st);
 int ss_launch(const SsParams &p, cudaStream_t st);
+void corr_moments_launch(const int32_t *r1, int n_frames, int row_len, int start, int step, int K, long long *acc, cudaStream_t st);
 void traj_moments_launch(const int32_t *rows, const int32_t *iters, int G, int max_rows, int lanes, int n_frames, long long *acc,
                          cudaStream_t st);
 void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const double *theory, int S, double M, double *ssq,
@@ -110,7 +111,19 @@ static int have_device()
 }
 
 extern "C" const char *scldpc_last_error(void) { return g_err; }
-extern "C" int scldpc_version(void) { return 100; }
+extern "C" int scldpc_version(void) { return 200; }
+#ifndef SCLDPC_SRC_HASH
+#define SCLDPC_SRC_HASH "unknown"
+#endif
+// "src=<sha256 prefix of all sources> built=<date time> cuda=<toolkit version> arch=sm_100a": lets a caller (and
+// __graft_entry__.build / tests/test_capi_load.py) prove that the loaded .so was compiled from the sources next to it
+extern "C" const char *scldpc_build_info(void)
+{
+    static char buf[160];
+    snprintf(buf, sizeof buf, "src=%s built=%s %s cuda=%d.%d arch=sm_100a", SCLDPC_SRC_HASH, __DATE__, __TIME__, CUDART_VERSION / 1000,
+             (CUDART_VERSION % 1000) / 10);
+    return buf;
+}
 extern "C" int scldpc_device_count(void)
 {
     int n = 0;
@@ -827,6 +840,21 @@ extern "C" int scldpc_bp_position_counts(const scldpc_dims_t *d, uint32_t flags,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(cudaMemcpyAsync(pos_cnt_dev, p.pos_cnt, bytes, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(pos_pairs_dev, p.pos_pairs, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- pairwise-complete moments behind DataFrame.corr() in calc_theta_explicit_ss_bounds (EST.py:161-189) ----
+extern "C" int scldpc_pairwise_moments_accumulate(const int32_t *r1_dev, int n_frames, int row_len, int start, int step, int K,
+                                                  int64_t *acc_dev, void *stream)
+{
+    if (!r1_dev || !acc_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if (n_frames < 0 || K < 1 || step < 1 || start < 0 || start + (long long)(K - 1) * step >= row_len)
+        return fail(SCLDPC_EINVAL, "sampled columns out of range");
+    int rc = have_device();
+    if (rc) return rc;
+    if (n_frames == 0) return 0;
+    corr_moments_launch(r1_dev, n_frames, row_len, start, step, K, reinterpret_cast<long long *>(acc_dev), static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
     return 0;
 }
 

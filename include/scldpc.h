@@ -85,6 +85,9 @@ typedef struct {
 
 const char *scldpc_last_error(void);
 int scldpc_version(void);
+/* "src=<hash> built=<date time> cuda=<version> arch=sm_100a"; <hash> = first 16 hex digits of sha256 over the .cu files of csrc (Makefile
+ * order), common.cuh and this header -- the same value `make -C csrc print-hash` prints for the sources on disk */
+const char *scldpc_build_info(void);
 /* number of CUDA devices visible (0 => every compute call fails); never throws */
 int scldpc_device_count(void);
 
@@ -241,6 +244,14 @@ int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *vn_cn_dev, c
  * np.nansum(axis=0)).  r1_dev has row_len columns. */
 int scldpc_peel_variance_accumulate(const int32_t *r1_dev, int n_frames, int row_len, const double *theory_dev, int S,
                                     double M, double *ssq_dev, int64_t *counts_dev, void *stream);
+/* The reduction behind DataFrame.corr() in calc_theta_explicit_ss_bounds / _ppd (fl_scaling/est_scaling_params.py:161-189,
+ * :211-243): for the K sampled columns c_i = start + i*step of r1_dev [n_frames][row_len] (zeros are "missing"), accumulates
+ * (+=) into acc_dev int64 [4][K][K] the pairwise-complete moments  N_ij = #{f: X_fi != 0 and X_fj != 0},
+ * Sx_ij = sum_f X_fi [X_fj != 0], Sxx_ij = sum_f X_fi^2 [X_fj != 0], Sxy_ij = sum_f X_fi X_fj, from which
+ * corr_ij = (N Sxy - Sx_ij Sx_ji) / sqrt((N Sxx_ij - Sx_ij^2)(N Sxx_ji - Sx_ji^2)).  Exact integers, additive over chunks and
+ * ranks.  Works for peeling r1 trajectories and for the dVNs column of BP trajectory rows alike. */
+int scldpc_pairwise_moments_accumulate(const int32_t *r1_dev, int n_frames, int row_len, int start, int step, int K,
+                                       int64_t *acc_dev, void *stream);
 /* the 32-bit draws behind the picks of one frame (host function; used to feed the reference the same pick sequence) */
 void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uint32_t *out_host);
 

@@ -83,3 +83,10 @@ def test_header_is_plain_c_and_a_c_client_links_and_fails_loudly_without_a_gpu(t
         assert r.returncode == 2 and "no CUDA device" in r.stderr
     else:
         assert r.returncode == 0 and r.stdout.startswith("frames 16")
+
+
+def test_library_was_built_from_the_sources_on_disk():
+    """scldpc_build_info carries the hash of the sources the .so was compiled from; it must be the hash of csrc/ as it is now"""
+    from fl_scaling_sc_ldpc_b200 import _lib
+    info = _lib.lib().scldpc_build_info().decode()
+    assert "arch=sm_100a" in info and ("src=" + _lib.source_hash()) in info, info

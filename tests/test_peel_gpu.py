@@ -253,3 +253,32 @@ def test_variance_accumulation_matches_the_reference_function():
         ssq, cnt = pdx.calc_nu_chunk_device([torch.as_tensor(r1[lo:hi]).cuda()], theory, M)
         assert np.array_equal(cnt, z[f"cnt{k}"]), k
         assert np.array_equal(ssq, z[f"ssq{k}"]), k                  # float64, same summation order: exact
+
+
+def test_pairwise_complete_correlation_matches_pandas():
+    """the reduction of calc_theta_explicit_ss_bounds (EST.py:161-189): DataFrame(zeros -> NaN).corr() over sampled steps,
+    from exact device-side moment matrices accumulated over two chunks; and the theta fit built on it"""
+    import pandas as pd
+    from fl_scaling_sc_ldpc_b200 import est_scaling_params as esp
+    rng = np.random.default_rng(9)
+    F, S, M = 400, 260, 100
+    # AR(1)-like integer trajectories with a known correlation length, zeros (finished frames) towards the end
+    z = np.zeros((F, S))
+    z[:, 0] = rng.normal(size=F)
+    for t in range(1, S):
+        z[:, t] = 0.93 * z[:, t - 1] + np.sqrt(1 - 0.93 ** 2) * rng.normal(size=F)
+    r1 = np.maximum(1, np.rint(60 + 9 * z)).astype(np.int32)
+    for f in range(F):
+        r1[f, rng.integers(150, S + 60):] = 0
+    start, stop, ivl = 20, 220, 3
+    acc = esp.pairwise_moments([torch.as_tensor(r1[:150]).cuda(), torch.as_tensor(r1[150:]).cuda()], start, stop, ivl)
+    c = esp.corr_from_moments(acc)
+    x = r1[:, start:stop:ivl].astype(float) / M
+    x[x == 0] = np.nan
+    ref = pd.DataFrame(x).corr().to_numpy()
+    assert c.shape == ref.shape and np.allclose(c, ref, rtol=0, atol=1e-12, equal_nan=True)
+    n = acc[0].cpu().numpy()
+    assert n.max() == F and n.min() < F and (n == n.T).all()
+    # the fit the reference runs on that matrix (EST.py:211-243), same code path on the same numbers
+    theta = esp.calc_theta_explicit_ss_bounds_ppd(r1, 20, 140, M)
+    assert 0.03 < theta < 0.15                                      # -ln(0.93) = 0.0726 per step
