@@ -177,64 +177,7 @@ __global__ void __launch_bounds__(256) bp_cn_sweep_kernel(BpParams p)
     bp_cn_sweep_body<DC, TRAJ, FREEZE>(p, g);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// lane retirement, run by the last block of a VN sweep for its graph
-// ------------------------------------------------------------------------------------------------------------
-template <bool TRAJ>
-__device__ void bp_retire_lanes(const BpParams &p, int g)
-{
-    __shared__ u64 s_stop[SCLDPC_MAX_WORDS], s_act[SCLDPC_MAX_WORDS];
-    __shared__ int s_alive;
-    if (threadIdx.x == 0) s_alive = 0;
-    __syncthreads();
-    for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
-        const u64 a = p.active[g * p.W + w];
-        const u64 nw = ld_cg(p.any_new + g * p.W + w);
-        const u64 er = ld_cg(p.any_er + g * p.W + w);
-        u64 stop = a & ~er;                                            // NumErasures == 0
-        if (!p.first_iter || p.stall_at_first) stop |= a & ~nw;        // NumErasures == NumErasuresPrec
-        if (p.iter + 1 >= p.max_it) stop = a;                          // while (iter < MaxNumIt)
-        s_stop[w] = stop;
-        s_act[w] = a;
-        const u64 left = a & ~stop;
-        p.active[g * p.W + w] = left;
-        p.any_new[g * p.W + w] = 0;
-        p.any_er[g * p.W + w] = 0;
-        if (left) s_alive = 1;
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
-        const int w = l >> 6, b = l & 63;
-        if ((s_stop[w] >> b) & 1ull) {
-            p.iters[g * p.lanes + l] += p.iter + 1;
-            p.work[g * p.lanes + l] += (long long)(p.iter + 1) * p.win_edges;
-        }
-        if (TRAJ) {
-            int dvn = 0, d1 = 0;
-            for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
-                const size_t o = ((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l;
-                dvn += ld_cg(p.cnt_dvn + o);
-                d1 += ld_cg(p.cnt_deg1 + o);
-                p.cnt_dvn[o] = 0;
-                p.cnt_deg1[o] = 0;
-            }
-            if (((s_act[w] >> b) & 1ull) && p.row >= 0 && p.row < p.max_rows) {
-                int first = p.L;                                        // first_erased = n => prints L (BP_TRAJ.c:1017,1051)
-                for (int q = 0; q < p.L; q++)
-                    if ((ld_cg(p.pos_er + ((size_t)g * p.L + q) * p.W + w) >> b) & 1ull) { first = q; break; }
-                int *r = p.rows + (((size_t)g * p.max_rows + p.row) * p.lanes + l) * 3;
-                r[0] = d1; r[1] = dvn; r[2] = first;
-            }
-        }
-    }
-    __syncthreads();
-    if (TRAJ)
-        for (int i = threadIdx.x; i < p.L * p.W; i += blockDim.x) p.pos_er[(size_t)g * p.L * p.W + i] = 0;
-    if (threadIdx.x == 0) {
-        p.ticket[g] = 0;
-        if (!s_alive) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
-    }
-}
+// (bp_retire_lanes: common.cuh)
 
 // ------------------------------------------------------------------------------------------------------------
 // variable-node sweep + decision + stop flags
@@ -384,147 +327,7 @@ __global__ void __launch_bounds__(256) bp_window_persistent_kernel(BpParams p0, 
 // kernels.  Checked bit for bit against the message kernels, the oracle and the compiled decodeBP_SW (tests/test_bp_parity_gpu.py:
 // residual, P1, blocks, expurgated counts, erased VNs; 1920 random cases of a numpy restatement incl. per-window iterations).
 // ------------------------------------------------------------------------------------------------------------
-template <int DV, int DC, bool HEAD>
-__global__ void __launch_bounds__(256, 4) bpw_cn_node_kernel(BpParams p)
-{
-    static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
-    pdl_wait_then_release();
-    const int g = blockIdx.y;
-    if (ld_cg(p.alive + g) == 0) return;
-    const int ch = p.chunks;
-    const int k = threadIdx.x & (ch - 1);
-    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    if (!nz(act)) return;                                       // a thread keeps its chunk
-    const u128 *__restrict__ xk = p.x + (size_t)g * p.n * ch + k;
-    unsigned *__restrict__ xbk = reinterpret_cast<unsigned *>(p.xb + (size_t)g * p.n * ch + k);
-    const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
-    const int items = (p.c1 - p.c0) << p.chunk_shift;
-    const int stride = gridDim.x * blockDim.x;
-    const int E = p.E;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += stride) {
-        const int32_t *row = cn_edge + (size_t)(p.c0 + (idx >> p.chunk_shift)) * DC;
-        int e[DC];
-        load_row<DC>(row, e);
-        u128 in[DC];
-#pragma unroll
-        for (int j = 0; j < DC; j++) in[j] = (e[j] != E) ? ld_stream(xk + (unsigned)((e[j] / DV) << p.chunk_shift)) : zero128();
-        u128 one = zero128(), tw = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
-#pragma unroll
-        for (int j = 0; j < DC; j++) {
-            tw |= one & in[j];
-            one |= in[j];
-            if (j & 1) b0 |= in[j];
-            if (j & 2) b1 |= in[j];
-            if (j & 4) b2 |= in[j];
-            if (j & 8) b3 |= in[j];
-        }
-        u128 res = one & ~tw & act;                             // exactly one erased neighbour, frame still iterating
-        if (HEAD && p.c0 + (idx >> p.chunk_shift) < p.cn_dis_lim) {
-            // Unscanned head of simulate_sc_ldpc (is_bounded = False): a slot below the scan start is only decoded when a
-            // removal leaves it with one user (PD.py:308-311), so a CN that starts with exactly one erased neighbour never
-            // resolves it (same plane as bp_cn_wave_kernel<.,.,HEAD>)
-            u128 *dp = p.cn_dis + ((size_t)g * p.cn_dis_lim + p.c0 + (idx >> p.chunk_shift)) * ch + k;
-            u128 dis;
-            if (p.first_iter) { dis = one & ~tw; *dp = dis; }
-            else dis = *dp;
-            res &= ~dis;
-        }
-        if (nz(res)) {
-            const unsigned rw[4] = {(unsigned)res.x, (unsigned)(res.x >> 32), (unsigned)res.y, (unsigned)(res.y >> 32)};
-            const unsigned w0[4] = {(unsigned)b0.x, (unsigned)(b0.x >> 32), (unsigned)b0.y, (unsigned)(b0.y >> 32)};
-            const unsigned w1[4] = {(unsigned)b1.x, (unsigned)(b1.x >> 32), (unsigned)b1.y, (unsigned)(b1.y >> 32)};
-            const unsigned w2[4] = {(unsigned)b2.x, (unsigned)(b2.x >> 32), (unsigned)b2.y, (unsigned)(b2.y >> 32)};
-            const unsigned w3[4] = {(unsigned)b3.x, (unsigned)(b3.x >> 32), (unsigned)b3.y, (unsigned)(b3.y >> 32)};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                unsigned m = rw[q];
-                while (m) {
-                    const int b = __ffs((int)m) - 1;
-                    m &= m - 1;
-                    int j = ((w0[q] >> b) & 1u) | (((w1[q] >> b) & 1u) << 1) | (((w2[q] >> b) & 1u) << 2);
-                    if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
-                    const unsigned o = (unsigned)((__ldg(row + j) / DV) << p.chunk_shift);
-                    atomicAnd(xbk + 4 * (size_t)o + q, ~(1u << b));
-                }
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 4) bpw_vn_node_kernel(BpParams p)
-{
-    pdl_wait_then_release();
-    const int g = blockIdx.y;
-    if (ld_cg(p.alive + g) == 0) return;
-    __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
-    __shared__ int s_last;
-    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_new[threadIdx.x] = 0; s_er[threadIdx.x] = 0; }
-    __syncthreads();
-    const int ch = p.chunks;
-    const int k = threadIdx.x & (ch - 1);
-    const u128 act = reinterpret_cast<const u128 *>(p.active)[g * ch + k];
-    u128 acc_new = zero128(), acc_er = zero128();
-    u128 *__restrict__ x = p.x + ((size_t)g * p.n + p.v0) * ch;
-    const u128 *__restrict__ xb = p.xb + ((size_t)g * p.n + p.v0) * ch;
-    const int items = (p.v1 - p.v0) << p.chunk_shift;
-    const int stride = gridDim.x * blockDim.x;
-    constexpr int U = 4;                                        // rows in flight per thread: a plain stream, latency-bound otherwise
-    if (nz(act))
-        for (int base = blockIdx.x * blockDim.x * U + threadIdx.x; base < items; base += stride * U) {
-            u128 xos[U], xbs[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int idx = base + u * (int)blockDim.x;
-                xos[u] = zero128(); xbs[u] = zero128();
-                if (idx < items) { xos[u] = x[idx]; xbs[u] = ld_cg128(xb + idx); }   // the CN sweep wrote xb with atomics (L2)
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int idx = base + u * (int)blockDim.x;
-                if (idx >= items) break;
-                const u128 xo = xos[u];
-                const u128 xn = sel(act, xbs[u], xo);
-                if (neq(xn, xo)) x[idx] = xn;
-                // a window's first iteration compares with NumErasuresPrecTerm = n: "progress" = some VN of the range is known
-                acc_new |= (p.first_iter ? ~xn : (xo & ~xn)) & act;
-                acc_er |= xn & act;
-            }
-        }
-    acc_new = warp_or_same_chunk(acc_new, ch);
-    acc_er = warp_or_same_chunk(acc_er, ch);
-    if ((threadIdx.x & 31) < ch) {
-        if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
-        if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
-        if (acc_er.x) atomicOr(&s_er[2 * k], acc_er.x);
-        if (acc_er.y) atomicOr(&s_er[2 * k + 1], acc_er.y);
-    }
-    __syncthreads();
-    if (threadIdx.x < p.W) {
-        const int w = threadIdx.x;
-        if (s_new[w] & ~ld_cg(p.any_new + g * p.W + w)) atomicOr(p.any_new + g * p.W + w, s_new[w]);
-        if (s_er[w] & ~ld_cg(p.any_er + g * p.W + w)) atomicOr(p.any_er + g * p.W + w, s_er[w]);
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket + g, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        bp_retire_lanes<false>(p, g);
-    }
-}
-
-// x = xb = channel erasures (Lji = channel value on every edge, Lij = 1: BP_SW.c:650-659)
-__global__ void bpw_node_init_kernel(BpParams p)
-{
-    const size_t items = (size_t)p.G * p.n * p.chunks;
-    const u128 *chan = reinterpret_cast<const u128 *>(p.chan);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (size_t)gridDim.x * blockDim.x) {
-        const u128 c = chan[i];
-        p.x[i] = c;
-        p.xb[i] = c;
-    }
-}
+// (the node-state window kernels live in bp_window_node_kernels.cu)
 
 // ------------------------------------------------------------------------------------------------------------
 // finalisation: per-position erasure counts, size-two stopping sets, per-frame results
@@ -757,48 +560,6 @@ static void launch_iteration(const BpParams &p, bool traj, bool freeze, cudaStre
         cudaEventRecord(ev[2], st);
         g_prof.iter_idx[g_prof.n_samples++] = p.iter;
     }
-}
-
-template <int DV, int DC>
-static void launch_window_node_iteration(const BpParams &p, cudaStream_t st, int blocks_per_sm)
-{
-    const int block = 256;
-    dim3 gc = sweep_grid((long long)(p.c1 - p.c0) << p.chunk_shift, p.G, block, blocks_per_sm);
-    dim3 gv = sweep_grid((((long long)(p.v1 - p.v0) << p.chunk_shift) + 3) / 4, p.G, block, blocks_per_sm);   // four rows per thread and trip
-    const bool sample = g_prof.sample_every > 0 && g_prof.n_samples < g_prof.max_samples && (p.iter % g_prof.sample_every) == 0;
-    cudaEvent_t *ev = sample ? g_prof.ev + 3 * g_prof.n_samples : nullptr;
-    if (sample) cudaEventRecord(ev[0], st);
-    g_prof.launches += (p.c1 > p.c0) ? 2 : 1;
-    // programmatic dependent launches inside a window / a call; its first kernel follows ordinary ones
-    static const bool pdl_on = getenv("SCLDPC_NO_PDL") == nullptr;
-    const bool pdl = pdl_on && !sample;
-    if (p.c1 > p.c0) {
-        if (p.cn_dis_lim > 0) launch_pdl(bpw_cn_node_kernel<DV, DC, true>, gc, dim3(block), st, pdl && !p.first_iter, p);
-        else launch_pdl(bpw_cn_node_kernel<DV, DC, false>, gc, dim3(block), st, pdl && !p.first_iter, p);
-    }
-    if (sample) cudaEventRecord(ev[1], st);
-    launch_pdl(bpw_vn_node_kernel, gv, dim3(block), st, pdl && (p.c1 > p.c0 || !p.first_iter), p);
-    if (sample) {
-        cudaEventRecord(ev[2], st);
-        g_prof.iter_idx[g_prof.n_samples++] = p.iter;
-    }
-}
-
-int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm)
-{
-    if (dv == 4 && dc == 8) launch_window_node_iteration<4, 8>(p, st, blocks_per_sm);
-    else if (dv == 3 && dc == 6) launch_window_node_iteration<3, 6>(p, st, blocks_per_sm);
-    else if (dv == 5 && dc == 10) launch_window_node_iteration<5, 10>(p, st, blocks_per_sm);
-    else if (dv == 3 && dc == 9) launch_window_node_iteration<3, 9>(p, st, blocks_per_sm);
-    else if (dv == 4 && dc == 12) launch_window_node_iteration<4, 12>(p, st, blocks_per_sm);
-    else return -1;
-    return 0;
-}
-
-void bp_launch_window_node_init(const BpParams &p, cudaStream_t st)
-{
-    g_prof.launches += 1;
-    bpw_node_init_kernel<<<num_sms() * 8, 256, 0, st>>>(p);
 }
 
 template <int DV, int DC>

@@ -42,62 +42,14 @@
 #ifndef NS_VARIANT
 #define NS_VARIANT 0
 #endif
+// NS_PREFETCH = 1 fetches the index row of the next trip while this trip's gathers are in flight.  The row load is 16 % of the
+// stall samples (profiles/r02c), but with 32 resident warps per SM other warps cover it: measured 52.2 us per launch with the
+// prefetch against 50.1 us without (gpurun_out/r2d_variants.log) -- off.
 #ifndef NS_PREFETCH
-#define NS_PREFETCH 1
+#define NS_PREFETCH 0
 #endif
 
 namespace scldpc {
-
-__device__ __forceinline__ uint2 ld_cg_u2(const uint2 *p)
-{
-    uint2 r;
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st_cg_u2(uint2 *p, uint2 v)
-{
-    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
-}
-
-// fire-and-forget AND at L2.  atomicAnd() with an unused result compiled to ATOMG (with a response) here, not to RED.
-__device__ __forceinline__ void red_and(unsigned *p, unsigned v)
-{
-    asm volatile("red.global.and.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// replay of one warp's region of the previous launch on plane `w` (32-bit words of graph g)
-__device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int par_prev, unsigned *w, int rid, bool zero_count)
-{
-    const int RW = NS_MAX_BLOCKS * NS_WARPS;
-    int *cntp = p.nl_cnt + (size_t)(g * 2 + par_prev) * RW + rid;
-    const int cnt = ld_cg(cntp);
-    const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * NS_WCAP;
-    // eight independent loads in flight per thread (a region holds ~200 entries): one L2 round trip instead of seven
-    constexpr int U = 8;
-    for (int i0 = threadIdx.x & 31; i0 < cnt; i0 += 32 * U) {
-        uint2 e[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) e[u] = (i0 + 32 * u < cnt) ? ld_cg_u2(reg + i0 + 32 * u) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (e[u].y) red_and(w + e[u].x, ~e[u].y);
-    }
-    if (zero_count && (threadIdx.x & 31) == 0) *cntp = 0;
-}
-
-// catch-up after an overflow: w &= r on the whole plane (r is the plane the overflowing launch wrote, complete by now)
-__device__ __forceinline__ void ns_catch_up(const BpParams &p, const u128 *r, u128 *w)
-{
-    const int items = p.n << p.chunk_shift;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
-        const u128 rv = ld_cg128(r + i), wv = ld_cg128(w + i);
-        const unsigned rr[4] = {(unsigned)rv.x, (unsigned)(rv.x >> 32), (unsigned)rv.y, (unsigned)(rv.y >> 32)};
-        const unsigned ww[4] = {(unsigned)wv.x, (unsigned)(wv.x >> 32), (unsigned)wv.y, (unsigned)(wv.y >> 32)};
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (ww[q] & ~rr[q]) red_and(reinterpret_cast<unsigned *>(w + i) + q, rr[q]);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // one flooding iteration: replay, check-node sweep, end of the iteration (last block)
@@ -127,11 +79,11 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     const u128 *__restrict__ rd = (par ? p.xb : p.x) + plane;
     u128 *__restrict__ wr = (par ? p.x : p.xb) + plane;
     unsigned *__restrict__ wr32 = reinterpret_cast<unsigned *>(wr);
-    const int RW = NS_MAX_BLOCKS * NS_WARPS;
+    const int RW = p.nl_rw;
     const int rid = blockIdx.x * NS_WARPS + warp;
 
     // ---- the write plane catches up with the previous iteration ----
-    if (ld_cg(p.nl_ovf + g * 2 + (par ^ 1))) ns_catch_up(p, rd, wr);
+    if (ld_cg(p.nl_ovf + g * 2 + (par ^ 1))) ns_catch_up(rd, wr, 0, p.n << p.chunk_shift);
     else if (!(NS_VARIANT & 4)) ns_replay_region(p, g, par ^ 1, wr32, rid, false);
 
     // ---- check-node sweep ----
@@ -299,12 +251,12 @@ __global__ void __launch_bounds__(32 * NS_WARPS) ns_settle_kernel(BpParams p)
     __shared__ int s_ovf;
     if (threadIdx.x == 0) s_ovf = ld_cg(p.nl_ovf + g * 2 + par_prev);
     __syncthreads();
-    if (s_ovf) ns_catch_up(p, rd, wr);
+    if (s_ovf) ns_catch_up(rd, wr, 0, p.n << p.chunk_shift);
     else ns_replay_region(p, g, par_prev, reinterpret_cast<unsigned *>(wr), blockIdx.x * NS_WARPS + (threadIdx.x >> 5), true);
 }
 __global__ void ns_settle_done_kernel(BpParams p)
 {
-    const int RW = NS_MAX_BLOCKS * NS_WARPS;
+    const int RW = p.nl_rw;
     const int g = blockIdx.x, par_prev = (p.iter & 1) ^ 1;
     if (ld_cg(p.nl_ovf + g * 2 + par_prev) == 0) return;
     for (int i = threadIdx.x; i < RW; i += blockDim.x) p.nl_cnt[(size_t)(g * 2 + par_prev) * RW + i] = 0;

@@ -27,7 +27,8 @@ void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st);
 void bp_launch_node_arm(const BpParams &p, cudaStream_t st);
 void bp_launch_node_tables(const BpParams &p, cudaStream_t st);
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
-void bp_launch_window_node_init(const BpParams &p, cudaStream_t st);
+void bp_launch_window_node_init(const BpParams &p, cudaStream_t st, bool resume);
+int bp_launch_window_node_end(int dv, int dc, const BpParams &p, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
 int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
@@ -148,6 +149,15 @@ struct Carve {
 
 static int env_int(const char *name, int dflt, int lo, int hi);
 
+// regions of the per-warp resolution lists: one per warp of the largest sweep grid (items = nodes x chunks, 256 per block)
+static size_t list_regions(size_t max_nodes, size_t ch)
+{
+    size_t blocks = (max_nodes * ch + 255) / 256;
+    if (blocks > NS_MAX_BLOCKS) blocks = NS_MAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    return blocks * NS_WARPS;
+}
+
 static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *p)
 {
     const size_t G = d->n_graphs, W = d->n_words, ch = W / 2, lanes = 64 * W;
@@ -195,7 +205,8 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         q.ex2 = c.take<u128>(G * nk * ch);
         q.first_new = c.take<u64>(G * W);
         if (no_msgs) {
-            const size_t RW = (size_t)NS_MAX_BLOCKS * NS_WARPS;
+            const size_t RW = list_regions(nk, ch);
+            q.nl_rw = (int)RW;
             q.noprog = c.take<u64>(G * W);
             q.cn_row = c.take<int32_t>(G * nk * d->dc);
             q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
@@ -204,6 +215,17 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         }
     }
     q.cn_dis = (flags & SCLDPC_F_STREAM) ? nullptr : c.take<u128>(G * nk * ch);   // sized for the largest possible ignored head
+    if (!(flags & (SCLDPC_F_STREAM | SCLDPC_F_MESSAGES | SCLDPC_F_TRAJECTORY))) {
+        // node-state window decoder / synchronous full BP (bp_window_node_kernels.cu): per-warp resolution lists
+        const size_t RW = list_regions(nk > n / 4 ? nk : n / 4, ch);
+        q.nl_rw = (int)RW;
+        q.noprog = c.take<u64>(G * W);
+        q.win_known = c.take<u64>(G * W);
+        q.nl_last = c.take<int>(G);
+        q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
+        q.nl_cnt = c.take<int>(G * 2 * RW);
+        q.nl_ovf = c.take<int>(G * 2);
+    }
     if (p) *p = q;
     return c.off;
 }
@@ -486,8 +508,9 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     const bool node = !traj && d->n_frames > 0 && !(flags & SCLDPC_F_MESSAGES);
     if (node) {
         p.xb = p.y;
+        p.win_lists = 1;                         // the sweep covers the whole chain: few rows change per iteration
         bp_launch_init_ctrl_only(p, d->n_frames, st);
-        bp_launch_window_node_init(p, st);
+        bp_launch_window_node_init(p, st, false);
     } else bp_launch_init(p, d->dv, d->dc, traj, d->n_frames, st);
     CU(cudaGetLastError());
     p.c0 = 0;
@@ -505,6 +528,7 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     p.cn_pos_lim = term ? d->L + d->dv - 1 : d->L;
     if (wave) bp_launch_wave_init(p, st);
     if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, wave, st, &launched, node))) return rc;
+    if (node && bp_launch_window_node_end(d->dv, d->dc, p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   (flags & SCLDPC_F_EXP_ALL) ? 1 : 0, 1, 0};
     if (d->n_frames == 0) CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
@@ -588,7 +612,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     CU(cudaMemsetAsync(p.x, 0, sizeof(u128) * plane, st));
     CU(cudaMemsetAsync(p.first_new, 0, sizeof(u64) * (size_t)p.G * p.W, st));
     if (node) {
-        const size_t RW = (size_t)NS_MAX_BLOCKS * NS_WARPS;
+        const size_t RW = (size_t)p.nl_rw;
         CU(cudaMemsetAsync(p.xb, 0, sizeof(u128) * plane, st));
         CU(cudaMemsetAsync(p.noprog, 0, sizeof(u64) * (size_t)p.G * p.W, st));
         CU(cudaMemsetAsync(p.nl_cnt, 0, sizeof(int) * (size_t)p.G * 2 * RW, st));
@@ -714,8 +738,11 @@ static int bp_window_impl(const scldpc_dims_t *d, const scldpc_batch_t *b, int W
     const bool node = !(flags & SCLDPC_F_MESSAGES) && d->n_frames > 0;
     if (node) {
         p.xb = pending_dev ? reinterpret_cast<u128 *>(pending_dev) : p.y;   // the wave-tracking plane is free in window mode
+        // resolution lists pay when few rows change per iteration, i.e. when the window is long against the wave (about 10
+        // positions); short windows copy the VN window instead (bp_window_node_kernels.cu)
+        p.win_lists = env_int("SCLDPC_WINDOW_LISTS", (long long)(W + ms) * 2 >= L ? 1 : 0, 0, 1);
         bp_launch_init_ctrl_only(p, d->n_frames, st);
-        if (!resume) bp_launch_window_node_init(p, st);
+        bp_launch_window_node_init(p, st, resume != 0);
     } else {
         bp_launch_init(p, d->dv, d->dc, 0, d->n_frames, st);
         CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));
@@ -754,6 +781,7 @@ static int bp_window_impl(const scldpc_dims_t *d, const scldpc_batch_t *b, int W
             persistent = false;
             if ((rc = run_iterations(&p, d->dv, d->dc, NumIt, false, true, false, st, nullptr, node))) return rc;
         }
+        if (node && bp_launch_window_node_end(d->dv, d->dc, p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
     }
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   1, square ? ms : 0, square ? W - 2 : W - 2 - ms};   // posW in [ms, W-2] (BP_SW.c:846-847)

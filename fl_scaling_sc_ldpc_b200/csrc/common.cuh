@@ -57,6 +57,22 @@ __device__ __forceinline__ u128 ld_cg128(const u128 *p)
     return r;
 }
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
+__device__ __forceinline__ uint2 ld_cg_u2(const uint2 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_cg_u2(uint2 *p, uint2 v)
+{
+    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+// fire-and-forget AND at L2.  atomicAnd() with an unused result sometimes compiles to ATOMG (with a response), not to RED:
+// measured +18 us per sweep of the node-state stream kernel (profiles/README.md, round 2).
+__device__ __forceinline__ void red_and(unsigned *p, unsigned v)
+{
+    asm volatile("red.global.and.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // OR-reduce a u128 over the threads of a warp that share (threadIdx.x % chunks); chunks is a power of two <= 8
 __device__ __forceinline__ u128 warp_or_same_chunk(u128 v, int chunks)
@@ -236,10 +252,15 @@ struct BpParams {
     u64 *noprog;              // [G][W] node-state streams: lanes that stopped because an iteration resolved nothing (see bp_node_kernels.cu)
     int32_t *cn_row;          // [G][nk][dc] node-state streams: x-plane row offset (v << chunk_shift) of each CN edge; absent edges
                               //   point at the all-zero row behind the last graph's plane
-    uint2 *nl_list;           // [G][2][NS_MAX_BLOCKS*NS_WARPS][NS_WCAP] node-state streams: (32-bit word of the plane, bits cleared) per
+    uint2 *nl_list;           // [G][2][nl_rw][NS_WCAP] node-state sweeps: (32-bit word of the plane, bits cleared) per
                               //   resolution of the previous iteration, one private region per warp of the sweep's grid
-    int *nl_cnt;              // [G][2][NS_MAX_BLOCKS*NS_WARPS] entries in each region
+    int *nl_cnt;              // [G][2][nl_rw] entries in each region
+    int nl_rw;                // regions per graph and parity: 8 warps x blocks of the largest sweep, at most NS_MAX_BLOCKS*NS_WARPS
     int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
+    int *nl_last;             // [G] node-state window decoder: last iteration the graph executed in the current window
+    u64 *win_known;           // [G][W] node-state window decoder: lanes in which the channel left some VN known
+    int win_lists;            // node-state window decoder: 1 = resolution lists (one launch per iteration, bp_window_node_kernels.cu),
+                              //   0 = copy variant (CN sweep + copy of the VN window)
     int lazy_success;         // 1: "no erased VN is left" is not tracked per iteration; a frame that finishes stops one iteration
                               //   later on "nothing resolved" and the harvest takes that iteration off again
     u64 *fail_mask;           // [G][W] subset of done_mask that stopped with erased VNs left (the only lanes the count kernels read)
@@ -266,6 +287,99 @@ struct BpParams {
     int row;                  // trajectory row written by this iteration (-1: none)
     long long win_edges;      // edge updates of one iteration of the current sweep ranges
 };
+
+// ---- per-warp resolution lists of the node-state sweeps (bp_node_kernels.cu, bp_window_node_kernels.cu) ----------------
+// replay of one warp's region of the previous launch on plane `w` (32-bit words of graph g)
+__device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int par_prev, unsigned *w, int rid, bool zero_count)
+{
+    const int RW = p.nl_rw;
+    int *cntp = p.nl_cnt + (size_t)(g * 2 + par_prev) * RW + rid;
+    const int cnt = ld_cg(cntp);
+    const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * NS_WCAP;
+    // eight independent loads in flight per thread (a region holds ~200 entries): one L2 round trip instead of seven
+    constexpr int U = 8;
+    for (int i0 = threadIdx.x & 31; i0 < cnt; i0 += 32 * U) {
+        uint2 e[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) e[u] = (i0 + 32 * u < cnt) ? ld_cg_u2(reg + i0 + 32 * u) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (e[u].y) red_and(w + e[u].x, ~e[u].y);
+    }
+    if (zero_count && (threadIdx.x & 31) == 0) *cntp = 0;
+}
+
+// catch-up after an overflow: w &= r on rows [i0, i1) of the plane (r is the plane the overflowing launch wrote, complete by now)
+__device__ __forceinline__ void ns_catch_up(const u128 *r, u128 *w, int i0, int i1)
+{
+    for (int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += gridDim.x * blockDim.x) {
+        const u128 rv = ld_cg128(r + i), wv = ld_cg128(w + i);
+        const unsigned rr[4] = {(unsigned)rv.x, (unsigned)(rv.x >> 32), (unsigned)rv.y, (unsigned)(rv.y >> 32)};
+        const unsigned ww[4] = {(unsigned)wv.x, (unsigned)(wv.x >> 32), (unsigned)wv.y, (unsigned)(wv.y >> 32)};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (ww[q] & ~rr[q]) red_and(reinterpret_cast<unsigned *>(w + i) + q, rr[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// lane retirement, run by the last block of a VN sweep for its graph
+// ------------------------------------------------------------------------------------------------------------
+template <bool TRAJ>
+__device__ __forceinline__ void bp_retire_lanes(const BpParams &p, int g)
+{
+    __shared__ u64 s_stop[SCLDPC_MAX_WORDS], s_act[SCLDPC_MAX_WORDS];
+    __shared__ int s_alive;
+    if (threadIdx.x == 0) s_alive = 0;
+    __syncthreads();
+    for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
+        const u64 a = p.active[g * p.W + w];
+        const u64 nw = ld_cg(p.any_new + g * p.W + w);
+        const u64 er = ld_cg(p.any_er + g * p.W + w);
+        u64 stop = a & ~er;                                            // NumErasures == 0
+        if (!p.first_iter || p.stall_at_first) stop |= a & ~nw;        // NumErasures == NumErasuresPrec
+        if (p.iter + 1 >= p.max_it) stop = a;                          // while (iter < MaxNumIt)
+        s_stop[w] = stop;
+        s_act[w] = a;
+        const u64 left = a & ~stop;
+        p.active[g * p.W + w] = left;
+        p.any_new[g * p.W + w] = 0;
+        p.any_er[g * p.W + w] = 0;
+        if (left) s_alive = 1;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_stop[w] >> b) & 1ull) {
+            p.iters[g * p.lanes + l] += p.iter + 1;
+            p.work[g * p.lanes + l] += (long long)(p.iter + 1) * p.win_edges;
+        }
+        if (TRAJ) {
+            int dvn = 0, d1 = 0;
+            for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
+                const size_t o = ((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l;
+                dvn += ld_cg(p.cnt_dvn + o);
+                d1 += ld_cg(p.cnt_deg1 + o);
+                p.cnt_dvn[o] = 0;
+                p.cnt_deg1[o] = 0;
+            }
+            if (((s_act[w] >> b) & 1ull) && p.row >= 0 && p.row < p.max_rows) {
+                int first = p.L;                                        // first_erased = n => prints L (BP_TRAJ.c:1017,1051)
+                for (int q = 0; q < p.L; q++)
+                    if ((ld_cg(p.pos_er + ((size_t)g * p.L + q) * p.W + w) >> b) & 1ull) { first = q; break; }
+                int *r = p.rows + (((size_t)g * p.max_rows + p.row) * p.lanes + l) * 3;
+                r[0] = d1; r[1] = dvn; r[2] = first;
+            }
+        }
+    }
+    __syncthreads();
+    if (TRAJ)
+        for (int i = threadIdx.x; i < p.L * p.W; i += blockDim.x) p.pos_er[(size_t)g * p.L * p.W + i] = 0;
+    if (threadIdx.x == 0) {
+        p.ticket[g] = 0;
+        if (!s_alive) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
+    }
+}
 
 // Per-frame result pointers of the finalisation kernels.
 struct BpFinalOut {

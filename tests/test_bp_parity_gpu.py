@@ -101,11 +101,15 @@ def test_full_bp_extreme_channels():
         check_bp(eng.decode_bp_full(fb, 0, is_term, trajectory=True, max_rows=32), ref, rows=True)
 
 
-@pytest.fixture(params=["node_state", "two_launches", "persistent"])
+@pytest.fixture(params=["node_state", "node_lists", "node_copy", "two_launches", "persistent"])
 def window_mode(request, monkeypatch):
-    """the window decoder in node-state form (default), with message-passing sweeps as two launches per iteration, and
-    with message-passing sweeps as one cooperative launch per window"""
-    monkeypatch.setenv("SCLDPC_WINDOW_NODE", "1" if request.param == "node_state" else "0")
+    """the window decoder in node-state form (default: resolution lists for long windows, copy of the VN window for short
+    ones; both forced here), with message-passing sweeps as two launches per iteration, and with message-passing sweeps as
+    one cooperative launch per window"""
+    monkeypatch.setenv("SCLDPC_WINDOW_NODE", "1" if request.param.startswith("node") else "0")
+    monkeypatch.delenv("SCLDPC_WINDOW_LISTS", raising=False)
+    if request.param in ("node_lists", "node_copy"):
+        monkeypatch.setenv("SCLDPC_WINDOW_LISTS", "1" if request.param == "node_lists" else "0")
     if request.param == "persistent":
         monkeypatch.setenv("SCLDPC_PERSISTENT", "1")
     else:

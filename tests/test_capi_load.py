@@ -37,9 +37,12 @@ def test_argument_validation_needs_no_gpu():
     assert L.scldpc_bp_workspace_bytes(ctypes.byref(bad), 0) == 0
     ok = _lib.Dims(4, 8, 10, 50, 25, 2, 2, 100)
     n, nk, E = 500, 13 * 25, 2000
-    need = L.scldpc_bp_workspace_bytes(ctypes.byref(ok), 0)
+    need = L.scldpc_bp_workspace_bytes(ctypes.byref(ok), _lib.F_MESSAGES)
     assert need >= 2 * ((E + 1) * 16 + nk * 8 * 16)   # the two message arrays dominate
-    assert L.scldpc_bp_workspace_bytes(ctypes.byref(ok), _lib.F_TRAJECTORY) > need
+    assert L.scldpc_bp_workspace_bytes(ctypes.byref(ok), _lib.F_TRAJECTORY) > need          # + the CNresolved latch
+    # the layout is a function of the flags alone: a size query and a call with the same flags agree
+    assert L.scldpc_bp_workspace_bytes(ctypes.byref(ok), 0) == L.scldpc_bp_workspace_bytes(ctypes.byref(ok), 0)
+    assert L.scldpc_bp_stream_workspace_bytes(ctypes.byref(ok), 0) != L.scldpc_bp_stream_workspace_bytes(ctypes.byref(ok), _lib.F_MESSAGES)
 
 
 def test_no_cpu_fallback():

@@ -8,6 +8,6 @@ make -s -j8
 for v in "$@"; do
   if [ "$v" = np ]; then def="-DNS_PREFETCH=0"; name=np; else def="-DNS_VARIANT=$v"; name=v$v; fi
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -I../../include $def -c bp_node_kernels.cu -o /tmp/bp_node_kernels_$name.o
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libscldpc_$name.so capi.o bp_kernels.o bp_wave_kernels.o /tmp/bp_node_kernels_$name.o ss_kernels.o traj_kernels.o corr_kernels.o graph_kernels.o peel_kernels.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libscldpc_$name.so capi.o bp_kernels.o bp_wave_kernels.o /tmp/bp_node_kernels_$name.o bp_window_node_kernels.o ss_kernels.o traj_kernels.o corr_kernels.o graph_kernels.o peel_kernels.o
   echo built libscldpc_$name.so
 done
