@@ -27,7 +27,7 @@ EXPORTS = [
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
     "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_bp_window_range", "scldpc_decode_host",
     "scldpc_graph_generate_at", "scldpc_channel_generate_at",
-    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets", "scldpc_bp_trajectory_moments", "scldpc_pairwise_moments_accumulate",
+    "scldpc_bp_stream_workspace_bytes", "scldpc_bp_stream", "scldpc_stream_host", "scldpc_bp_position_counts", "scldpc_bp_stopping_sets", "scldpc_bp_trajectory_moments", "scldpc_pairwise_moments_accumulate", "scldpc_allreduce_counters",
     "scldpc_peel_workspace_bytes", "scldpc_peel_trajectories", "scldpc_peel_variance_accumulate", "scldpc_philox_picks",
     "scldpc_launch_count", "scldpc_profile_begin", "scldpc_profile_end", "scldpc_bp_sweep_stats",
 ]

@@ -936,6 +936,30 @@ extern "C" int scldpc_bp_stopping_sets(const scldpc_dims_t *d, const scldpc_batc
     return 0;
 }
 
+// ---- multi-GPU: the only collective of the path ------------------------------------------------------------------------
+// Sum of an int64 counter / accumulator vector over the ranks of a caller-owned NCCL communicator (the reference merges its
+// per-process files offline with awk / pickle sums, NB:565, NB:1195, notebook cell 23).  NCCL is resolved at call time with
+// dlopen, so the library has no link-time dependency on it and uses the NCCL the calling process has already loaded.
+#include <dlfcn.h>
+extern "C" int scldpc_allreduce_counters(void *nccl_comm, int64_t *counters_dev, int n_int64, void *stream)
+{
+    if (!nccl_comm || !counters_dev || n_int64 < 0) return fail(SCLDPC_EINVAL, "NULL communicator / buffer");
+    if (n_int64 == 0) return 0;
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    static allreduce_fn fn = nullptr;
+    if (!fn) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(SCLDPC_ECUDA, "NCCL not found: %s", dlerror());
+        fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+        if (!fn) return fail(SCLDPC_ECUDA, "ncclAllReduce not found in libnccl");
+    }
+    const int nccl_int64 = 4, nccl_sum = 0;      // ncclDataType_t / ncclRedOp_t values of nccl.h (stable ABI)
+    const int rc = fn(counters_dev, counters_dev, (size_t)n_int64, nccl_int64, nccl_sum, nccl_comm, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return fail(SCLDPC_ECUDA, "ncclAllReduce failed with ncclResult_t %d", rc);
+    return 0;
+}
+
 // ---- instrumentation --------------------------------------------------------------------------------------------
 // Positions swept by the last scldpc_bp_full call on this workspace, summed over graphs and iterations:
 // out[0] = CN positions, out[1] = VN positions (a sweep of everything would be iterations*(L+dv-1) and iterations*L).

@@ -255,6 +255,13 @@ int scldpc_pairwise_moments_accumulate(const int32_t *r1_dev, int n_frames, int 
 /* the 32-bit draws behind the picks of one frame (host function; used to feed the reference the same pick sequence) */
 void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uint32_t *out_host);
 
+/* ---- multi-GPU ------------------------------------------------------------------------------------------- */
+/* Frames shard trivially (global graph / frame ids, no data-path collective); the one exchange is the sum of the final
+ * counter or accumulator vectors -- what the reference does offline with awk / pickle sums over its per-process files
+ * (NB:565, NB:1195, notebook cell 23).  nccl_comm: the caller's ncclComm_t; counters_dev: int64 [n_int64], reduced in
+ * place on `stream`.  NCCL is resolved with dlopen at call time (no link-time dependency). */
+int scldpc_allreduce_counters(void *nccl_comm, int64_t *counters_dev, int n_int64, void *stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* kernels launched by the library since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
  * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change) */

@@ -53,3 +53,36 @@ def test_two_ranks_reproduce_single_process(tmp_path):
                 assert np.array_equal(np.asarray(x), np.asarray(y)), n
         else:
             assert a == b, n
+
+
+def test_c_abi_allreduce_on_a_callers_nccl_communicator():
+    """scldpc_allreduce_counters with a raw ncclComm_t (a C caller's sharding path): a one-rank communicator created through
+    libnccl's own C API; the int64 vector comes back unchanged (sum over one rank) and the call is stream-ordered"""
+    import ctypes
+    import torch
+    from fl_scaling_sc_ldpc_b200 import _lib
+    try:
+        nccl = ctypes.CDLL("libnccl.so.2", mode=ctypes.RTLD_GLOBAL)
+    except OSError:
+        pytest.skip("libnccl.so.2 not loadable")
+    uid = (ctypes.c_char * 128)()
+    assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    comm = ctypes.c_void_p()
+
+    class Uid(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+    u = Uid.from_buffer_copy(bytes(uid))
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), 1, u, 0) == 0
+    try:
+        t = torch.arange(-3, 13, dtype=torch.int64, device="cuda") * (1 << 40)
+        ref = t.clone()
+        L = _lib.lib()
+        _lib.check(L.scldpc_allreduce_counters(comm, ctypes.c_void_p(t.data_ptr()), t.numel(),
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert bool((t == ref).all())
+        assert L.scldpc_allreduce_counters(None, ctypes.c_void_p(t.data_ptr()), 4, None) != 0
+    finally:
+        nccl.ncclCommDestroy(comm)
