@@ -23,7 +23,7 @@ F_MESSAGES = 64
 F_NO_WAVE = 128
 
 EXPORTS = [
-    "scldpc_last_error", "scldpc_version", "scldpc_build_info", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_generate",
+    "scldpc_last_error", "scldpc_version", "scldpc_build_info", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_build_tables_async", "scldpc_graph_generate",
     "scldpc_graph_generate_scratch_bytes", "scldpc_channel_generate", "scldpc_channel_pack_host",
     "scldpc_bp_workspace_bytes", "scldpc_bp_full", "scldpc_bp_window", "scldpc_bp_window_range", "scldpc_decode_host",
     "scldpc_graph_generate_at", "scldpc_channel_generate_at",

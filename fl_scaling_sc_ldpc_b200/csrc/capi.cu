@@ -315,6 +315,23 @@ extern "C" int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_ba
     return 0;
 }
 
+// The same without a host synchronisation: the validity flag (0 = fine, 1 = CN index out of range, 2 = a CN with more than dc
+// edges) is left in *err_dev for the caller to read when it next synchronises anyway.  Graphs drawn by scldpc_graph_generate
+// are valid by construction; the flag matters for injected graphs.
+extern "C" int scldpc_graph_build_tables_async(const scldpc_dims_t *d, const scldpc_batch_t *b, int32_t *scratch_dev, int32_t *err_dev,
+                                               void *stream)
+{
+    int rc = check_dims(d);
+    if (rc) return rc;
+    if (!b || !b->vn_cn_dev || !b->vn_slot_dev || !b->cn_edge_dev || !scratch_dev || !err_dev) return fail(SCLDPC_EINVAL, "NULL pointer");
+    if ((rc = have_device())) return rc;
+    const int n = d->L * d->vns_pos, nk = (d->L + d->dv - 1) * d->cns_pos;
+    graph_build_tables(b->vn_cn_dev, b->vn_slot_dev, b->cn_edge_dev, scratch_dev, err_dev, d->n_graphs, n, nk, d->dv, d->dc,
+                       static_cast<cudaStream_t>(stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int scldpc_graph_generate(const scldpc_dims_t *d, int32_t *vn_cn_dev, uint64_t *scratch_dev, uint64_t seed,
                                      uint64_t first_graph_id, int tail_biting, void *stream)
 {

@@ -95,6 +95,7 @@ class FrameBatch:
         self.cn_edge = torch.empty((G, ens.nk, ens.dc), dtype=torch.int32, device=dev)
         self.chan = torch.zeros((G, ens.n, W), dtype=torch.int64, device=dev)
         self._scratch = torch.empty((G, ens.nk), dtype=torch.int32, device=dev)
+        self._graph_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._keys = None
         self._ws = None
         self._ws_flags = None
@@ -123,7 +124,7 @@ class FrameBatch:
             _lib.check(L.scldpc_graph_generate_at(ctypes.byref(self.dims), ctypes.c_void_p(self.vn_cn.data_ptr()),
                                                   ctypes.c_void_p(self._keys.data_ptr()), ctypes.c_uint64(seed),
                                                   ctypes.c_uint64(first_graph_id), ctypes.c_uint32(first_position), _stream()))
-            self._build_tables()
+            self._build_tables(check=False)
             return self
         ensemble = 2 if protograph else int(bool(tail_biting))
         tail_biting = ensemble
@@ -133,12 +134,24 @@ class FrameBatch:
         _lib.check(L.scldpc_graph_generate(ctypes.byref(self.dims), ctypes.c_void_p(self.vn_cn.data_ptr()),
                                            ctypes.c_void_p(self._keys.data_ptr()), ctypes.c_uint64(seed),
                                            ctypes.c_uint64(first_graph_id), int(tail_biting), _stream()))
-        self._build_tables()
+        self._build_tables(check=False)
         return self
 
-    def _build_tables(self):
-        _lib.check(_lib.lib().scldpc_graph_build_tables(ctypes.byref(self.dims), ctypes.byref(self.cbatch),
-                                                        ctypes.c_void_p(self._scratch.data_ptr()), _stream()))
+    def _build_tables(self, check: bool = True):
+        """vn_slot / cn_edge from vn_cn.  ``check=False`` (graphs drawn by the library: valid by construction) stays
+        stream-ordered -- no host synchronisation, so a loop that redraws its graphs every batch never stalls the device;
+        the validity flag stays in ``self._graph_err`` (``graph_error()`` reads it)."""
+        if check:
+            _lib.check(_lib.lib().scldpc_graph_build_tables(ctypes.byref(self.dims), ctypes.byref(self.cbatch),
+                                                            ctypes.c_void_p(self._scratch.data_ptr()), _stream()))
+        else:
+            _lib.check(_lib.lib().scldpc_graph_build_tables_async(ctypes.byref(self.dims), ctypes.byref(self.cbatch),
+                                                                  ctypes.c_void_p(self._scratch.data_ptr()),
+                                                                  ctypes.c_void_p(self._graph_err.data_ptr()), _stream()))
+
+    def graph_error(self) -> int:
+        """validity flag of the last stream-ordered table build: 0 fine, 1 CN index out of range, 2 CN degree > dc"""
+        return int(self._graph_err.item())
 
     # ---- channel -----------------------------------------------------------------------------------------
     def set_erasures(self, erased) -> "FrameBatch":

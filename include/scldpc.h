@@ -95,6 +95,11 @@ int scldpc_device_count(void);
 /* Builds vn_slot / cn_edge from vn_cn on the device, CN rows in the order generate_code appends them
  * (BP_FULL.c:1702-1716).  Replaces the CNdegree half of generate_code.  scratch_dev: int32 [G][nk]. */
 int scldpc_graph_build_tables(const scldpc_dims_t *d, const scldpc_batch_t *b, int32_t *scratch_dev, void *stream);
+/* Stream-ordered form without the host synchronisation of the call above: the validity flag (0 = fine, 1 = CN index out of
+ * range, 2 = a CN with more than dc edges) is left in *err_dev (device int32) for the caller to read later.  Graphs drawn by
+ * scldpc_graph_generate are valid by construction, so a Monte-Carlo loop that redraws its graphs every batch
+ * (main_terminated, BP_FULL.c:2117-2143) never has to stop the device for them. */
+int scldpc_graph_build_tables_async(const scldpc_dims_t *d, const scldpc_batch_t *b, int32_t *scratch_dev, int32_t *err_dev, void *stream);
 
 /* On-device ensemble generation: the "Olmos random ensemble" of generate_code (BP_FULL.c:1656-1761) /
  * SC.gen_slots (SC.py:33-56): an independent uniform socket permutation per CN position.  Graph g of the batch

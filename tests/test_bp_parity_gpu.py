@@ -208,3 +208,25 @@ def test_trajectory_moments_on_the_device():
             assert not r.rows[:, :, t][~live].any()                   # rows of stopped frames are the zero padding
     assert (acc.cpu().numpy() == ref).all()
     assert ref[0, 0] == 2 * 228 and ref[-1, 0] < ref[0, 0]
+
+
+def test_stream_ordered_table_build_reports_validity_without_a_sync():
+    """scldpc_graph_build_tables_async: generated graphs are valid (flag 0) and decode like the checked build; a malformed
+    injected graph leaves the reference's two failure modes in the flag instead of raising"""
+    ens = eng.Ensemble(4, 8, 10, 32)
+    fb = eng.FrameBatch(ens, 2, 64).generate_graphs(3).generate_erasures(0.45, 4)
+    assert fb.graph_error() == 0
+    a = eng.decode_bp_full(fb, 0, True)
+    fb._build_tables(check=True)
+    b = eng.decode_bp_full(fb, 0, True)
+    assert (a.iters == b.iters).all() and (a.residual == b.residual).all()
+    good = fb.vn_cn.clone()
+    fb.vn_cn[1, 5, 2] = ens.nk + 7                    # CN index out of range
+    fb._build_tables(check=False)
+    assert fb.graph_error() == 1
+    fb.vn_cn.copy_(good)
+    fb.vn_cn[0, :9, 0] = fb.vn_cn[0, 0, 0]           # nine edges on one CN
+    fb._build_tables(check=False)
+    assert fb.graph_error() == 2
+    with pytest.raises(eng.ScldpcError):
+        fb._build_tables(check=True)
