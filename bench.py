@@ -57,6 +57,25 @@ def workload_name(fpg: int) -> str:
             f"4 new graphs x {fpg} frames per graph per step")
 
 
+def make_config(args) -> dict:
+    """The `config` object of the JSON line -- the same function (hence the same object) for both arms."""
+    stream_mode = args.mode == "stream"
+    lanes = 64 * N_WORDS
+    B = args.frames_per_graph if stream_mode else lanes
+    G = len(EPS_SWEEP) * args.graphs_per_eps
+    messages = os.environ.get("SCLDPC_STREAM_NODE" if stream_mode else "SCLDPC_FULL_NODE", "1") == "0"
+    # decoder state per batch: two planes of n x lanes bits, index tables, resolution lists, or the two message arrays
+    n_bits = L * M * lanes * G
+    state_mb = round(((2 * n_bits / 8) + (8 * E_EDGES + 4 * N_CNS * DC) * G * (0 if messages else 1) + (4 * E_EDGES * lanes / 8 * G if messages else 0)) / 2 ** 20)
+    return {"workload": workload_name(B), "frames_per_graph": B, "graphs_per_step_per_gpu": G,
+            "frames_per_step_per_gpu": G * B, "lanes_per_graph": lanes, "n_words": N_WORDS, "mode": args.mode,
+            "sweeps": "message passing" if messages else "node-state",
+            "graph_turnover": "new graphs every step, generated and indexed on the device inside the timed region; no "
+                              "(graph, frame) realisation is decoded twice",
+            "l2": f"inputs larger than L2 (126 MB): about {state_mb} MB of decoder state per batch, rewritten every step",
+            "seed": args.seed}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own decoders on the host cores
 # ------------------------------------------------------------------------------------------------------------------
@@ -205,7 +224,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": eu, "unit": "edge-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, len(per_step)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (0/1 messages)",
-        "data": "synthetic", "config": {"workload": workload_name(args.frames_per_graph)},
+        "data": "synthetic", "config": make_config(args),
         "frame_iterations_per_s": iters / t, "frames_per_s_at_348_iterations": iters / t / 348.0,
         "reference_libraries_loaded": loaded,
         "cpu_baseline": {"value": eu, "unit": "edge-updates/s", "cores": cores, "kind": kind, "sample": sample},
@@ -745,18 +764,11 @@ def run_ours(args):
             workloads = {"error": repr(e)}
 
     if rank == 0:
-        ws_mb = need / 2 ** 20
         line = {
             "metric": METRIC, "value": value, "unit": "edge-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (64 bit-sliced frames per word)", "data": "synthetic",
-            "config": {"workload": workload_name(B), "frames_per_graph": B, "graphs_per_step_per_gpu": G,
-                       "frames_per_step_per_gpu": G * B, "lanes_per_graph": lanes, "n_words": N_WORDS, "mode": args.mode,
-                       "sweeps": "message passing" if messages else "node-state",
-                       "graph_turnover": "new graphs every step, generated and indexed on the device inside the timed region; no "
-                                         "(graph, frame) realisation is decoded twice",
-                       "l2": f"inputs larger than L2: {ws_mb:.0f} MB of decoder state per batch, rewritten every step",
-                       "seed": args.seed},
+            "config": make_config(args),
             "frames_per_s": frames / (ms * 1e-3),
             "frame_iterations_per_s": frame_iters / (ms * 1e-3),
             "mean_iterations_per_frame": frame_iters / max(1, frames),
