@@ -492,7 +492,9 @@ def side_workloads(args, dev, side_cpu):
             work = 2 * r.edge_updates
             ach = work * (B_ALG / (2 * E_EDGES)) / dt / 1e9
             wl[f"W={W}"] = {"value": work / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
-                            "eps": e, "frame_error_rate": float((r.residual > 0).mean()), "gpu_launches": launches,
+                            "eps": e, "frame_error_rate": float((r.residual > 0).mean()),
+                            "undecoded_vn_fraction": float(r.residual.mean()) / (100 * M),     # non-terminated: the last positions stay erased
+                            "gpu_launches": launches,
                             "roofline": {"bound": "hbm", "kernel": "bpw_cn_node_kernel<4,8> + bpw_vn_node_kernel (window iterations)",
                                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                                          "traffic": (tj.get("window_node", {}) or {}).get(f"W{W}_dram_bytes_per_launch"),

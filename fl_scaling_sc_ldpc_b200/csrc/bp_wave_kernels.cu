@@ -598,7 +598,11 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
         // hint for the host's harvest period: mean iterations per harvested frame of the slowest graph still decoding
         p.h_cum[2 * g] += s_frames;
         p.h_cum[2 * g + 1] += (long long)s_its;
-        if (any && p.h_cum[2 * g] > 0) atomicMax(p.alive_total + 1 + p.harvest_parity, (int)(p.h_cum[2 * g + 1] / p.h_cum[2 * g]));
+        if (any && p.h_cum[2 * g] > 0) {
+            const int mean_it = (int)(p.h_cum[2 * g + 1] / p.h_cum[2 * g]);
+            atomicMax(p.alive_total + 1 + p.harvest_parity, mean_it);      // slowest graph still decoding
+            atomicMin(p.alive_total + 4 + p.harvest_parity, mean_it);      // fastest graph still decoding
+        }
     }
 }
 

@@ -177,7 +177,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
     q.pos_er = c.take<u64>(G * d->L * W);
     q.ticket = c.take<unsigned>(G);
     q.alive = c.take<int>(G);
-    q.alive_total = c.take<int>(4);
+    q.alive_total = c.take<int>(8);
     q.h_cum = c.take<long long>(G * 2);
     q.cnt_dvn = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
     q.cnt_deg1 = c.take<int>(G * SCLDPC_CNT_SLOTS * lanes);
@@ -662,9 +662,14 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     // re-armed lanes) and a finished frame idles H/2 iterations on average, so the best period is about sqrt(6 x iterations
     // per frame); measured flat between 3.5 and 10 at M = 10000.  harvest_every <= 0: adapt it to the frames harvested so far (the slowest graph still decoding); > 0: fixed.
     const bool adaptive = cfg->harvest_every <= 0;
+    // The period follows the FASTEST graph still decoding (SCLDPC_HARVEST_POLICY=1: the slowest, as in round 1): a harvest
+    // costs every live graph the same, an idle lane costs a fast graph a larger share of its frame.  Measured flat
+    // (profiles/r02h_harvest_period_ab.txt: 5.62 .. 5.82e13 edge-updates/s for constants 25 .. 60 and both policies).
     const int hc10 = env_int("SCLDPC_HARVEST_C10", 60, 1, 1000);
+    const int h_policy_max = env_int("SCLDPC_HARVEST_POLICY", 0, 0, 1);
     int H = adaptive ? 16 : cfg->harvest_every;
     CU(cudaMemsetAsync(p.alive_total + 1, 0, 2 * sizeof(int), st));
+    CU(cudaMemsetAsync(p.alive_total + 4, 0x7f, 2 * sizeof(int), st));
     CU(cudaMemsetAsync(p.h_cum, 0, sizeof(long long) * 2 * (size_t)p.G, st));
     long long it = 0;
     int nchunk = 0;
@@ -678,13 +683,16 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         const int slot = nchunk & 1;
         p.harvest_parity = slot;
         p.iter = (int)(it & 0x3fffffff);         // the iteration that runs next (its parity names the planes)
-        if (adaptive) CU(cudaMemsetAsync(p.alive_total + 1 + slot, 0, sizeof(int), st));
+        if (adaptive) {
+            CU(cudaMemsetAsync(p.alive_total + 1 + slot, 0, sizeof(int), st));
+            CU(cudaMemsetAsync(p.alive_total + 4 + slot, 0x7f, sizeof(int), st));
+        }
         if (node) bp_launch_node_settle(d->dv, d->dc, p, st);
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
         if (node) bp_launch_node_arm(p, st);
         CU_LAUNCHES();
-        CU(cudaMemcpyAsync(hf + 4 * slot, p.alive_total, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hf + 8 * slot, p.alive_total, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
         pending[slot] = true;
         nchunk++;
@@ -692,8 +700,9 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         if (pending[prev]) {
             CU(cudaEventSynchronize(ev[prev]));
             pending[prev] = false;
-            if (hf[4 * prev] == 0) break;
-            const int mean_it = hf[4 * prev + 1 + prev];
+            if (hf[8 * prev] == 0) break;
+            int mean_it = hf[8 * prev + 1 + prev];
+            if (!h_policy_max && hf[8 * prev + 4 + prev] != 0x7f7f7f7f) mean_it = hf[8 * prev + 4 + prev];
             if (adaptive && mean_it > 0) {
                 H = (int)(sqrt(0.1 * hc10 * mean_it) + 0.5);
                 H = H < 8 ? 8 : (H > 64 ? 64 : H);

@@ -223,7 +223,8 @@ struct BpParams {
     u64 *pos_er;              // [G][L][W] lanes with an erased VN in position p (trajectory mode)
     unsigned *ticket;         // [G]
     int *alive;               // [G] any active lane
-    int *alive_total;         // [4] graphs with an active lane; [1], [2]: largest mean iterations per harvested frame (by harvest parity)
+    int *alive_total;         // [8] graphs with an active lane; [1], [2]: largest, [4], [5]: smallest mean iterations per harvested frame
+                              //   among the graphs still decoding (by harvest parity)
     long long *h_cum;         // [G][2] frame streams: frames harvested so far and the iterations they took
     int harvest_parity;       // frame streams: which of alive_total[1..2] this harvest reports into
     int *cnt_dvn;             // [G][slots][lanes] newly resolved VNs of this iteration (trajectory mode)
