@@ -161,15 +161,15 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
                     if (DC > 8) j |= ((w3[q] >> b) & 1u) << 3;
                     const unsigned widx = 4u * ((unsigned)__ldg(row + j) + (unsigned)k) + (unsigned)q;   // L1 hit
                     red_and(wr32 + widx, ~(1u << b));
-                    if (!(NS_VARIANT & 2) && slot < NS_WCAP) st_cg_u2(reg + slot, make_uint2(widx, 1u << b));
+                    if (!(NS_VARIANT & 2) && slot < p.nl_cap) st_cg_u2(reg + slot, make_uint2(widx, 1u << b));
                     slot++;
                 }
             }
         }
     }
     if (lane == 0) {
-        p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < NS_WCAP ? wcount : NS_WCAP;
-        if (wcount > NS_WCAP) p.nl_ovf[g * 2 + par] = 1;
+        p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < p.nl_cap ? wcount : p.nl_cap;
+        if (wcount > p.nl_cap) p.nl_ovf[g * 2 + par] = 1;
     }
     acc_new = warp_or_same_chunk(acc_new, ch);
     if (lane < ch) {

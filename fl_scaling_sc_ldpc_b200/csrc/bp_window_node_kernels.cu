@@ -128,15 +128,15 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
                         entry = make_uint2(widx, 1u << b);
                         acc_new[q] |= 1u << b;
                     }
-                    if (slot < NS_WCAP) st_cg_u2(reg + slot, entry);
+                    if (slot < p.nl_cap) st_cg_u2(reg + slot, entry);
                     slot++;
                 }
             }
         }
     }
     if (lane == 0) {
-        p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < NS_WCAP ? wcount : NS_WCAP;
-        if (wcount > NS_WCAP) p.nl_ovf[g * 2 + par] = 1;
+        p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < p.nl_cap ? wcount : p.nl_cap;
+        if (wcount > p.nl_cap) p.nl_ovf[g * 2 + par] = 1;
     }
     u128 an = make_u128((u64)acc_new[0] | ((u64)acc_new[1] << 32), (u64)acc_new[2] | ((u64)acc_new[3] << 32));
     an = warp_or_same_chunk(an, ch);

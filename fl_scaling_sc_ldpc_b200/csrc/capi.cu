@@ -207,6 +207,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         if (no_msgs) {
             const size_t RW = list_regions(nk, ch);
             q.nl_rw = (int)RW;
+            q.nl_cap = env_int("SCLDPC_LIST_CAP", NS_WCAP, 1, NS_WCAP);   // test hook: does not change the layout
             q.noprog = c.take<u64>(G * W);
             q.cn_row = c.take<int32_t>(G * nk * d->dc);
             q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
@@ -219,6 +220,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         // node-state window decoder / synchronous full BP (bp_window_node_kernels.cu): per-warp resolution lists
         const size_t RW = list_regions(nk > n / 4 ? nk : n / 4, ch);
         q.nl_rw = (int)RW;
+        q.nl_cap = env_int("SCLDPC_LIST_CAP", NS_WCAP, 1, NS_WCAP);
         q.noprog = c.take<u64>(G * W);
         q.win_known = c.take<u64>(G * W);
         q.nl_last = c.take<int>(G);

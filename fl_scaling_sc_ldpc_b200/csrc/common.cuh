@@ -256,6 +256,7 @@ struct BpParams {
     uint2 *nl_list;           // [G][2][nl_rw][NS_WCAP] node-state sweeps: (32-bit word of the plane, bits cleared) per
                               //   resolution of the previous iteration, one private region per warp of the sweep's grid
     int *nl_cnt;              // [G][2][nl_rw] entries in each region
+    int nl_cap;               // entries of a region in use (NS_WCAP; SCLDPC_LIST_CAP lowers it so that tests reach the overflow path)
     int nl_rw;                // regions per graph and parity: 8 warps x blocks of the largest sweep, at most NS_MAX_BLOCKS*NS_WARPS
     int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
     int *nl_last;             // [G] node-state window decoder: last iteration the graph executed in the current window

@@ -53,9 +53,8 @@ def shard_graph_ids(first: int, count: int, rank: int | None = None, world_size:
 def allreduce_counters(values, device=None) -> np.ndarray:
     """Sum an int64 counter vector over all ranks (the job's only collective)."""
     t = torch.as_tensor(np.asarray(values, dtype=np.int64))
-    if device is not None:
-        t = t.to(device)
     if world()[1] > 1:
+        t = t.to(device if device is not None else _comm_device())    # NCCL reduces device tensors, gloo host tensors
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
 
@@ -71,9 +70,8 @@ def broadcast_int(value: int) -> int:
 
 def allreduce_max(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64)
-    if device is not None:
-        t = t.to(device)
     if world()[1] > 1:
+        t = t.to(device if device is not None else _comm_device())
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 

@@ -5,7 +5,7 @@
  * and called by tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py
  * and by nothing else.  The product library (libscldpc.so) never links or calls it.
  *
- * Parity status: PINNED.  Every function below is checked (tests/test_oracle_vs_ref.py) against the
+ * Parity status: PINNED.  Every function below is checked (tests/test_oracle_golden.py) against the
  * unmodified reference C code compiled from /root/reference by oracle/build_ref.py (same glibc random()
  * stream => identical graphs, channels, decisions, counters and trajectory rows), and against the golden
  * vectors under tests/golden/ that were generated from that compiled reference.

@@ -144,3 +144,39 @@ def test_stream_matches_oracle_directly():
                     o = oracle.decode_bp(gg, ch[g, f].astype(np.int32), 10 ** 9, int(is_term))
                     got = (s.iters[g, f0 + f], s.residual[g, f0 + f], s.blocks_err[g, f0 + f], s.erasures_exp[g, f0 + f], s.blocks_err_exp[g, f0 + f])
                     assert got == (o["iters"], o["residual"], o["blocks_err"], o["erasures_exp"], o["blocks_err_exp"]), (is_term, g, f0 + f)
+
+
+@pytest.mark.parametrize("cap", [1, 7])
+def test_resolution_list_overflow_falls_back_to_a_full_pass(cap, monkeypatch, stream_kernels):
+    """per-warp resolution lists hold 1024 entries per iteration; a region that overflows flags the iteration and the next
+    launch catches up with a pass over the plane.  SCLDPC_LIST_CAP forces that path on small graphs, for the stream kernel
+    and for the list variant of the window / synchronous full-BP kernels"""
+    if stream_kernels == "messages":
+        pytest.skip("message-passing sweeps keep no lists")
+    ens = eng.Ensemble(4, 8, 12, 48)
+    fbg = eng.FrameBatch(ens, 2, 320).generate_graphs(29, first_graph_id=3)
+    eps = [0.45, 0.50]
+    ref = sync_reference(fbg, ens, 700, eps, 6, True)
+    monkeypatch.setenv("SCLDPC_LIST_CAP", str(cap))
+    for H in (1, 9):
+        s = eng.decode_bp_stream(fbg, 700, eps, 6, first_graph_id=3, harvest_every=H)
+        for key in KEYS:
+            assert (getattr(s, key) == ref[key]).all(), (H, key)
+    sc = eng.decode_bp_stream(fbg, 300, eps, 6, first_graph_id=3, max_it=5)
+    monkeypatch.delenv("SCLDPC_LIST_CAP")
+    sc_ref = eng.decode_bp_stream(fbg, 300, eps, 6, first_graph_id=3, max_it=5)
+    for key in KEYS:
+        assert (getattr(sc, key) == getattr(sc_ref, key)).all(), key
+    # synchronous full BP and a long window (list variant) with overflowing regions
+    fb = eng.FrameBatch(ens, 2, 128)
+    fb.vn_cn.copy_(fbg.vn_cn); fb._build_tables()
+    fb.generate_erasures(eps, 6, first_graph_id=3)
+    a = eng.decode_bp_full(fb, 0, True)
+    w = eng.decode_bp_window(fb, 9, 4, 10)
+    monkeypatch.setenv("SCLDPC_LIST_CAP", str(cap))
+    monkeypatch.setenv("SCLDPC_WINDOW_LISTS", "1")
+    b = eng.decode_bp_full(fb, 0, True)
+    w2 = eng.decode_bp_window(fb, 9, 4, 10)
+    for key in KEYS:
+        assert (getattr(a, key) == getattr(b, key)).all() and (getattr(w, key) == getattr(w2, key)).all(), key
+    assert bool((a.erased_words == b.erased_words).all()) and bool((w.erased_words == w2.erased_words).all())
