@@ -510,7 +510,7 @@ def side_workloads(args, dev, side_cpu):
 
     # ---- config 1: peeling trajectories
     if want is None or "peeling" in want:
-        for Mp, G, F in ((1000, 8, 1024), (10000, 2, 256)):
+        for Mp, G, F in ((1000, 16, 1024), (10000, 8, 1024)):
             l, r, Lp, e = 4, 8, 50, 0.48
             ensp = eng.Ensemble(l, r, Lp, Mp)
             cns, num_positions, total_size, steps = pdx._peel_geometry(e, l, r, Lp, Mp, False)

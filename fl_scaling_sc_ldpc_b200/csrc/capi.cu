@@ -42,7 +42,7 @@ void channel_generate(u64 *chan, int G, int n, int W, int n_frames, int vns_pos,
 void channel_pack(const uint8_t *bytes_dev, u64 *chan, int G, int n, int W, int F, cudaStream_t st);
 void bits_unpack(const u64 *bits, uint8_t *bytes_dev, int G, int n, int W, int F, cudaStream_t st);
 void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out);
-int peel_grid(int total_size, long long total_frames);
+int peel_grid(int total_size, long long total_frames, int n_cn_all);
 size_t peel_state_words(int n_cn_all, int total_size);
 int peel_launch(PeelParams p, int grid, cudaStream_t st);
 int ss_launch(const SsParams &p, cudaStream_t st);
@@ -835,7 +835,7 @@ extern "C" void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uin
 extern "C" size_t scldpc_peel_workspace_bytes(const scldpc_dims_t *d, int n_cn_all, int total_size)
 {
     if (check_dims(d) || have_device()) return 0;
-    const int grid = peel_grid(total_size, (long long)d->n_graphs * d->n_frames);
+    const int grid = peel_grid(total_size, (long long)d->n_graphs * d->n_frames, n_cn_all);
     if (grid < 0) { fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap"); return 0; }
     return sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size);
 }
@@ -852,7 +852,7 @@ extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *v
     if ((rc = have_device())) return rc;
     const long long frames = (long long)d->n_graphs * d->n_frames;
     if (frames == 0) return 0;
-    const int grid = peel_grid(total_size, frames);
+    const int grid = peel_grid(total_size, frames, n_cn_all);
     if (grid < 0) return fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap");
     if (workspace_bytes < sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size)) return fail(SCLDPC_ENOMEM, "workspace too small");
     PeelParams p;

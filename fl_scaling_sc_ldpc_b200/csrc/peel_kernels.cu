@@ -56,22 +56,27 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     return v;
 }
 
-// one warp per block; dynamic shared memory: [bitmap words |] level-1 counts | level-2 counts.  When the bitmap does not
-// fit next to the counts (M = 1e5: 2.5e6 CNs = 312 KB) it lives in global memory behind the block's CN state (it is
-// touched by a handful of words per step and stays L2-resident); the counts always stay in shared memory.
-__global__ void __launch_bounds__(32) peel_trajectory_kernel(PeelParams p)
+// One warp per frame, PEEL_WPB independent warps per block (a step is a chain of three dependent global round trips -- CN
+// state, adjacency row, degree updates -- so throughput is warps in flight / latency: 64 warps per SM instead of the 32 that
+// one-warp blocks allow).  Dynamic shared memory per warp: [bitmap words |] level-1 counts | level-2 counts.  When a
+// warp's bitmap does not leave room for 64 frames per SM it lives in global memory behind the warp's CN state (it is touched
+// by a handful of words per step); the counts always stay in shared memory.
+#define PEEL_WPB 2
+__global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelParams p)
 {
-    extern __shared__ unsigned s_mem[];
-    const int lane = threadIdx.x;
-    const size_t st_words = (size_t)p.n_cn_all + (p.bits_global ? ((size_t)p.n_words1 + 1) / 2 : 0);   // u64 per block
-    u64 *st = p.state + (size_t)blockIdx.x * st_words;
+    extern __shared__ unsigned s_mem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * PEEL_WPB + warp, n_slots = gridDim.x * PEEL_WPB;
+    unsigned *s_mem = s_mem_all + (size_t)warp * ((p.bits_global ? 0 : p.n_words1) + p.n_l1 + p.n_l2);
+    const size_t st_words = (size_t)p.n_cn_all + (p.bits_global ? ((size_t)p.n_words1 + 1) / 2 : 0);   // u64 per warp
+    u64 *st = p.state + (size_t)slot * st_words;
     unsigned *bits = p.bits_global ? reinterpret_cast<unsigned *>(st + p.n_cn_all) : s_mem;
     int *l1 = reinterpret_cast<int *>(s_mem + (p.bits_global ? 0 : p.n_words1));
     int *l2 = l1 + p.n_l1;
     const int l2q = (p.n_l2 + 31) / 32;                           // level-2 entries per lane
     const long long total_frames = (long long)p.G * p.n_frames;
 
-    for (long long fr = blockIdx.x; fr < total_frames; fr += gridDim.x) {
+    for (long long fr = slot; fr < total_frames; fr += n_slots) {
         const int g = (int)(fr / p.n_frames), f = (int)(fr % p.n_frames);
         const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * p.dv;
         const u64 *chan = p.chan + (size_t)g * p.n * p.W + (f >> 6);
@@ -218,7 +223,7 @@ size_t peel_smem_bytes(int total_size, int *n_words1, int *n_l1, int *n_l2, int 
     if (n_words1) *n_words1 = w;
     if (n_l1) *n_l1 = a;
     if (n_l2) *n_l2 = b;
-    size_t limit = 96 * 1024;                                                // keep >= 2 frames per SM in flight
+    size_t limit = 3400;                                                     // 64 frames per SM in flight (227 KB / 64)
     if (const char *e = getenv("SCLDPC_PEEL_SMEM_LIMIT")) limit = (size_t)atol(e);   // tests force the global-bitmap path
     const bool big = sizeof(unsigned) * ((size_t)w + a + b) > limit;
     if (bits_global) *bits_global = big ? 1 : 0;
@@ -233,7 +238,8 @@ size_t peel_state_words(int n_cn_all, int total_size)
     return (size_t)n_cn_all + (big ? ((size_t)w + 1) / 2 : 0);
 }
 
-int peel_grid(int total_size, long long total_frames)
+// number of frames decoded concurrently (= warps of the launch = CN-state slots of the workspace)
+int peel_grid(int total_size, long long total_frames, int n_cn_all)
 {
     int dev = 0, sms = 148, max_smem = 227 * 1024;
     cudaGetDevice(&dev);
@@ -242,21 +248,25 @@ int peel_grid(int total_size, long long total_frames)
     int n_l2 = 0;
     const size_t smem = peel_smem_bytes(total_size, nullptr, nullptr, &n_l2, nullptr);
     if (smem > (size_t)max_smem || n_l2 > 32 * 8) return -1;
-    long long per_sm = (long long)(max_smem) / (long long)(smem + 1024);
-    if (per_sm > 32) per_sm = 32;
+    long long per_sm = (long long)(max_smem) / (long long)(smem + 64);
+    if (per_sm > 64) per_sm = 64;
     if (per_sm < 1) per_sm = 1;
     long long grid = per_sm * sms;
+    // keep the CN-state workspace (8 B per CN and frame in flight) under 24 GB: M = 1e5 holds 21 MB per frame
+    const long long by_mem = (24ll << 30) / (8ll * (long long)peel_state_words(n_cn_all, total_size));
+    if (grid > by_mem) grid = by_mem;
     if (grid > total_frames) grid = total_frames;
-    return (int)(grid < 1 ? 1 : grid);
+    grid = (grid + PEEL_WPB - 1) / PEEL_WPB * PEEL_WPB;          // whole blocks
+    return (int)(grid < PEEL_WPB ? PEEL_WPB : grid);
 }
 
 int peel_launch(PeelParams p, int grid, cudaStream_t st)
 {
     const size_t smem = peel_smem_bytes(p.total_size, &p.n_words1, &p.n_l1, &p.n_l2, &p.bits_global);
     if (p.n_l2 > 32 * 8) return -1;                              // more than 2^23 CNs: one more level would be needed
-    if (cudaFuncSetAttribute(peel_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(peel_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * PEEL_WPB)) != cudaSuccess) return -2;
     g_prof.launches += 1;
-    peel_trajectory_kernel<<<grid, 32, smem, st>>>(p);
+    peel_trajectory_kernel<<<grid / PEEL_WPB, 32 * PEEL_WPB, smem * PEEL_WPB, st>>>(p);
     return 0;
 }
 

@@ -178,10 +178,16 @@ def test_bench_step_sample_matches_oracle_port(ref_results):
     fbg = eng.FrameBatch(ens, 4, 4, 2).generate_graphs(seed=SEED, first_graph_id=0)
     vn = fbg.vn_cn.cpu().numpy()
     rng = np.random.default_rng(3)
+    jobs = []
     for g in range(4):
         gg = oracle.Graph(vn[g], 50, M, ens.cns_pos, DV, DC)
         for f in sorted(rng.choice(16384, 6 if g == 3 else 4, replace=False)):
-            ch = _frame_channel(ens, None, EPS[g], SEED + 1, g, int(f))
-            o = oracle.decode_bp(gg, ch.astype(np.int32), 10 ** 9, 1, max_rows=1)
-            got = tuple(int(getattr(s, k)[g, f]) for k in KEYS)
-            assert got == tuple(int(o[k]) for k in KEYS), (g, f, got)
+            jobs.append((g, int(f), gg, _frame_channel(ens, None, EPS[g], SEED + 1, g, int(f)).astype(np.int32)))
+    # the oracle port runs outside the GIL (ctypes): a thread per host core
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        outs = list(ex.map(lambda j: oracle.decode_bp(j[2], j[3], 10 ** 9, 1, max_rows=1), jobs))
+    for (g, f, _, _), o in zip(jobs, outs):
+        got = tuple(int(getattr(s, k)[g, f]) for k in KEYS)
+        assert got == tuple(int(o[k]) for k in KEYS), (g, f, got)
