@@ -465,7 +465,9 @@ def side_workloads(args, dev, side_cpu):
             "value": its * 2.0 * E_EDGES / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
             "cap": cap, "trajectory_rows_per_step": 4 * 1024 * cap, "gpu_launches": launches,
             "note": "channel generation, decode with (deg_1_iter, dVNs, first erased position) rows for every iteration, 4 graphs x 1024 frames",
-            "roofline": {"bound": "hbm", "kernel": "bp_cn_wave_kernel<8,true> + bp_vn_wave_kernel<4,true> (one flooding iteration, trajectory counters)",
+            "sweeps": "message passing" if os.environ.get("SCLDPC_FULL_NODE", "1") == "0" else "node-state",
+            "roofline": {"bound": "hbm", "kernel": ("bp_cn_wave_kernel<8,true> + bp_vn_wave_kernel<4,true>" if os.environ.get("SCLDPC_FULL_NODE", "1") == "0"
+                                                   else "bpw_iter_kernel<4,8,false,true>") + " (one flooding iteration with the trajectory counters)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
                          "avg_launch_ms": [float(cn_ms.mean()), float(vn_ms.mean())], "launches_sampled": int(len(cn_ms)),
                          "frame_iterations_per_launch": fi_per_launch, "algorithmic_bytes": "(4E+n)/8 B per useful frame-iteration"}}
@@ -478,7 +480,7 @@ def side_workloads(args, dev, side_cpu):
         fb = eng.FrameBatch(ensw, 4, 1024, 16, device=dev)
         fb.generate_graphs(seed=args.seed, first_graph_id=7 << 20)
         wl = {}
-        for W, e in ((3, 0.36), (5, 0.40), (10, 0.45)):
+        for W, e in ((3, 0.30), (5, 0.40), (10, 0.45)):
             def step(i, W=W, e=e):
                 fb.generate_erasures(e, args.seed + 1, first_graph_id=(7 << 20) + 4 * (i + 2))
                 res, erased, rows, _ = eng.decode_bp_window(fb, W, 8, 60, square=True, is_term=False, collect=False)

@@ -21,6 +21,7 @@ F_EXP_ALL = 8
 F_CHAN_PACKED = 16
 F_MESSAGES = 64
 F_NO_WAVE = 128
+F_NODE_TRAJ = 256
 
 EXPORTS = [
     "scldpc_last_error", "scldpc_version", "scldpc_build_info", "scldpc_device_count", "scldpc_graph_build_tables", "scldpc_graph_build_tables_async", "scldpc_graph_generate",

@@ -664,6 +664,20 @@ int bp_launch_finalize(int dv, int dc, const BpParams &p, const BpFinalOut &o, c
     return 0;
 }
 
+// erased VNs per (position, lane) of an arbitrary plane into `out` ([G][L][lanes], += ; every lane)
+void bp_launch_pos_count_of(const BpParams &p, const u128 *plane, int *out, cudaStream_t st)
+{
+    BpParams q = p;
+    q.x = const_cast<u128 *>(plane);
+    q.pos_cnt = out;
+    q.lane_mask = nullptr;
+    q.lazy_success = 0;
+    int bx = (p.vns_pos * p.chunks + 255) / 256;
+    if (bx > 8) bx = 8;
+    g_prof.launches += 1;
+    bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(q);
+}
+
 void bp_launch_init(const BpParams &p, int dv, int dc, int trajectory, int n_frames, cudaStream_t st)
 {
     dim3 g((unsigned)(num_sms() * 4 / (p.G > 0 ? p.G : 1) + 1), (unsigned)p.G);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     const bool lane_work = nz(act);                             // a thread keeps its chunk
     const u128 *__restrict__ rdk = rd + k;
     const int32_t *__restrict__ cn_row = p.cn_row + (size_t)g * p.nk * DC;
-    uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * NS_WCAP;
+    uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * p.nl_stride;
     const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept
     const int stride = gridDim.x * blockDim.x;
     int wcount = 0;                                             // entries this warp has logged (warp-uniform)

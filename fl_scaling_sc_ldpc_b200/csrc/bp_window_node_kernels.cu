@@ -25,8 +25,19 @@
 
 namespace scldpc {
 
-template <int DV, int DC, bool HEAD>
-__global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
+// TRAJ (synchronous full BP with trajectory rows, BP_TRAJ.c:901-1151): the rows need, per frame and iteration, the degree-one
+// counter, the newly resolved VNs and the first erased position.
+//  * deg_1_iter (BP_TRAJ.c:935-979): a CN counts the first time one of its outgoing messages is "known" (latch), and only if
+//    exactly one is.  With u erased neighbours in the read plane: no outgoing message is known for u >= 2, exactly one for
+//    u = 1, all of them for u = 0 -- so the CN latches when u <= 1 and counts iff u = 1, or u = 0 and it has a single edge.
+//    (The extrinsic messages can differ from the a-posteriori state only for a VN that this CN itself resolved, and then
+//    the CN has latched before.)  Counted per lane without atomics (LaneCounter, common.cuh).
+//  * dVNs, first erased position, NumErasures: per (position, lane) counters of erased VNs, initialised from the channel and
+//    decremented by the thread that actually clears a bit (atom.and returns the old word, so a VN resolved by two CNs in the
+//    same iteration is counted once).  The last block sums them per lane: NumErasures is exact, so frames stop in the
+//    iteration the reference stops in (no late "finished" stop, no end-of-window correction).
+template <int DV, int DC, bool HEAD, bool TRAJ>
+__global__ void __launch_bounds__(32 * NS_WARPS, TRAJ ? 3 : 4) bpw_iter_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
     pdl_wait_then_release();
@@ -34,7 +45,13 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
+    __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
+    __shared__ u128 s_planes[TRAJ ? LC_PLANES * 32 * NS_WARPS : 1];
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
+    if (TRAJ)
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
+    LaneCounter lc;
+    if (TRAJ) lc.clear();
     __syncthreads();
     const int ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
@@ -56,15 +73,16 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
     const bool lane_work = nz(act);                             // a thread keeps its chunk
     const u128 *__restrict__ rdk = rd + k;
     const int32_t *__restrict__ cn_edge = p.cn_edge + (size_t)g * p.nk * DC;
-    uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * NS_WCAP;
+    uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * p.nl_stride;
     const int items = (p.c1 - p.c0) << p.chunk_shift;
     const int stride = gridDim.x * blockDim.x;
     const int E = p.E;
     const unsigned lo = (unsigned)p.v0, span = (unsigned)(p.v1 - p.v0);
     int wcount = 0;                                             // entries this warp has logged (warp-uniform)
     unsigned acc_new[4] = {0u, 0u, 0u, 0u};                     // frames that resolved a VN of the VN window
-    for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
-        const int idx = base + lane;
+    int trip = 0;                                               // block-uniform trip count (the counter flush is a block-wide step)
+    for (int base = blockIdx.x * blockDim.x; base < items; base += stride, trip++) {
+        const int idx = base + threadIdx.x;
         u128 res = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
         const int c = p.c0 + (idx >> p.chunk_shift);
         const int32_t *row = cn_edge + (size_t)c * DC;
@@ -85,6 +103,18 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
                 if (j & 8) b3 |= in[j];
             }
             res = one & ~tw & act;                              // exactly one erased neighbour, frame still iterating
+            if (TRAJ) {
+                int deg = 0;
+#pragma unroll
+                for (int j = 0; j < DC; j++) deg += (e[j] != E);
+                if (deg > 0) {
+                    u128 *lp = p.latch + ((size_t)g * p.nk + c) * ch + k;
+                    const u128 lat = *lp;
+                    const u128 nl = lat | (~tw & act);
+                    if (neq(nl, lat)) *lp = nl;
+                    lc.add((deg == 1 ? ~tw : (one & ~tw)) & ~lat & act);
+                }
+            }
             if (HEAD && c < p.cn_dis_lim) {
                 // Unscanned head of simulate_sc_ldpc (is_bounded = False): a slot below the scan start is only decoded when a
                 // removal leaves it with one user (PD.py:308-311), so a CN that starts with exactly one erased neighbour never
@@ -96,6 +126,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
                 res &= ~dis;
             }
         }
+        if (TRAJ && (trip % 31) == 30) lane_counter_flush(lc, s_planes, s_cnt, ch);
         if (__ballot_sync(0xffffffffu, nz(res)) == 0u) continue;
         const int cnt = __popcll(res.x) + __popcll(res.y);
         int incl = cnt;
@@ -124,7 +155,13 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
                     uint2 entry = make_uint2(0u, 0u);
                     if (v - lo < span) {                         // a VN of the VN window: the only ones anybody will look at again
                         const unsigned widx = 4u * ((v << p.chunk_shift) + (unsigned)k) + (unsigned)q;
-                        red_and(wr32 + widx, ~(1u << b));
+                        if (!TRAJ) red_and(wr32 + widx, ~(1u << b));
+                        else if (slot >= p.nl_cap) {
+                            // (region full: clear and count in place; otherwise after the sweep, see below)
+                            const unsigned old = atomicAnd(wr32 + widx, ~(1u << b));
+                            if ((old >> b) & 1u)
+                                atomicSub(p.pos_pairs + ((size_t)g * p.L + v / (unsigned)p.vns_pos) * p.lanes + k * 128 + q * 32 + b, 1);
+                        }
                         entry = make_uint2(widx, 1u << b);
                         acc_new[q] |= 1u << b;
                     }
@@ -137,6 +174,32 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
     if (lane == 0) {
         p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < p.nl_cap ? wcount : p.nl_cap;
         if (wcount > p.nl_cap) p.nl_ovf[g * 2 + par] = 1;
+    }
+    if (TRAJ) {
+        // Clearing + counting of this iteration's resolutions, from the warp's own list: the thread whose atom.and finds the
+        // bit still set takes the VN off its position's count (a VN resolved by two CNs in one iteration is counted once).
+        // Done here rather than in the sweep so that eight atomics with a return value are in flight per thread -- in the
+        // sweep every trip waited for its own (161 -> see DESIGN.md section 5).
+        __syncwarp();
+        const int cnt = wcount < p.nl_cap ? wcount : p.nl_cap;
+        constexpr int U = 8;
+        for (int i0 = lane; i0 < cnt; i0 += 32 * U) {
+            uint2 e[U];
+            unsigned old[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) e[u] = (i0 + 32 * u < cnt) ? ld_cg_u2(reg + i0 + 32 * u) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int u = 0; u < U; u++) old[u] = e[u].y ? atomicAnd(wr32 + e[u].x, ~e[u].y) : 0u;
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (old[u] & e[u].y) {
+                    const unsigned row = e[u].x >> (2 + p.chunk_shift), kk = (e[u].x >> 2) & (unsigned)(ch - 1), qq = e[u].x & 3u;
+                    atomicSub(p.pos_pairs + ((size_t)g * p.L + row / (unsigned)p.vns_pos) * p.lanes + kk * 128 + qq * 32 + (__ffs((int)e[u].y) - 1), 1);
+                }
+        }
+        lane_counter_flush(lc, s_planes, s_cnt, ch);
+        for (int i = threadIdx.x; i < p.lanes; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(p.cnt_deg1 + ((size_t)g * SCLDPC_CNT_SLOTS + (blockIdx.x % SCLDPC_CNT_SLOTS)) * p.lanes + i, s_cnt[i]);
     }
     u128 an = make_u128((u64)acc_new[0] | ((u64)acc_new[1] << 32), (u64)acc_new[2] | ((u64)acc_new[3] << 32));
     an = warp_or_same_chunk(an, ch);
@@ -157,16 +220,48 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) bpw_iter_kernel(BpParams p)
     __threadfence();
     // ---- end of the iteration for graph g (bp_retire_lanes without the "no erasure left" test, see the file header) ----
     __shared__ u64 s_stop[SCLDPC_MAX_WORDS];
+    __shared__ u64 s_er[SCLDPC_MAX_WORDS], s_prog[SCLDPC_MAX_WORDS];
     __shared__ int s_alive;
     if (threadIdx.x == 0) s_alive = 0;
+    if (threadIdx.x < SCLDPC_MAX_WORDS) { s_er[threadIdx.x] = 0; s_prog[threadIdx.x] = 0; }
     __syncthreads();
+    if (TRAJ) {
+        // per lane: NumErasures, the row of this iteration (BP_TRAJ.c:988,1051), "an erased VN is left", "a VN was resolved"
+        for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+            int cur = 0, first = p.L;                                   // first_erased = n => prints L (BP_TRAJ.c:1017,1051)
+            for (int q = 0; q < p.L; q++) {
+                const int v = ld_cg(p.pos_pairs + ((size_t)g * p.L + q) * p.lanes + l);
+                if (v > 0 && first == p.L) first = q;
+                cur += v;
+            }
+            int d1 = 0;
+            for (int sl = 0; sl < SCLDPC_CNT_SLOTS; sl++) {
+                const size_t o = ((size_t)g * SCLDPC_CNT_SLOTS + sl) * p.lanes + l;
+                d1 += ld_cg(p.cnt_deg1 + o);
+                p.cnt_deg1[o] = 0;
+            }
+            const int prev = p.cnt_dvn[(size_t)g * SCLDPC_CNT_SLOTS * p.lanes + l];      // NumErasuresPrec
+            const int w = l >> 6, b = l & 63;
+            if ((p.active[g * p.W + w] >> b) & 1ull) {
+                if (p.row >= 0 && p.row < p.max_rows) {
+                    int *r = p.rows + (((size_t)g * p.max_rows + p.row) * p.lanes + l) * 3;
+                    r[0] = d1; r[1] = prev - cur; r[2] = first;
+                }
+                p.cnt_dvn[(size_t)g * SCLDPC_CNT_SLOTS * p.lanes + l] = cur;
+                if (cur > 0) atomicOr(reinterpret_cast<unsigned long long *>(&s_er[w]), 1ull << b);
+                if (prev != cur) atomicOr(reinterpret_cast<unsigned long long *>(&s_prog[w]), 1ull << b);
+            }
+        }
+        __syncthreads();
+    }
     for (int w = threadIdx.x; w < p.W; w += blockDim.x) {
         const u64 a = p.active[g * p.W + w];
         u64 nw = ld_cg(p.any_new + g * p.W + w);
         u64 stop = 0;
-        if (!p.first_iter) stop = a & ~nw;                              // NumErasuresTerm == NumErasuresPrecTerm
+        if (TRAJ) stop = a & (~s_er[w] | ~s_prog[w]);                   // NumErasures == 0 || == NumErasuresPrec (exact counts)
+        else if (!p.first_iter) stop = a & ~nw;                         // NumErasuresTerm == NumErasuresPrecTerm
         else if (p.stall_at_first) stop = a & ~(nw | p.win_known[g * p.W + w]);   // ... == n: nothing resolved and nothing known
-        p.noprog[g * p.W + w] |= stop;
+        if (!TRAJ) p.noprog[g * p.W + w] |= stop;
         if (p.iter + 1 >= p.max_it) stop = a;                           // while (iter < NumIt)
         s_stop[w] = stop;
         const u64 left = a & ~stop;
@@ -418,6 +513,13 @@ __global__ void bpw_node_init_kernel(BpParams p)
     flush();
 }
 
+// trajectory mode: NumErasuresPrec = n for every frame (BP_TRAJ.c:910); the per-position counts come from bp_pos_count_kernel
+__global__ void bpw_traj_init_kernel(BpParams p)
+{
+    const int g = blockIdx.x;
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) p.cnt_dvn[(size_t)g * SCLDPC_CNT_SLOTS * p.lanes + l] = p.n;
+}
+
 __global__ void bpw_node_reset_kernel(BpParams p, int zero_known)
 {
     const int RW = p.nl_rw;
@@ -442,7 +544,7 @@ static dim3 window_grid(const BpParams &p)
         int occ = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bpw_iter_kernel<DV, DC, false>, block, 0) != cudaSuccess || occ < 1) occ = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bpw_iter_kernel<DV, DC, false, false>, block, 0) != cudaSuccess || occ < 1) occ = 2;
         res = occ * (sms > 0 ? sms : 148);
         if (res > NS_MAX_BLOCKS) res = NS_MAX_BLOCKS;
     }
@@ -513,8 +615,9 @@ static void launch_window_node_iteration(const BpParams &p, cudaStream_t st)
     static const bool pdl_on = getenv("SCLDPC_NO_PDL") == nullptr;
     // programmatic dependent launches inside a window; its first kernel follows ordinary ones
     const bool pdl = pdl_on && !sample && !p.first_iter;
-    if (p.cn_dis_lim > 0) launch_pdl(bpw_iter_kernel<DV, DC, true>, grid, block, st, pdl, p);
-    else launch_pdl(bpw_iter_kernel<DV, DC, false>, grid, block, st, pdl, p);
+    if (p.traj_node) launch_pdl(bpw_iter_kernel<DV, DC, false, true>, grid, block, st, pdl, p);
+    else if (p.cn_dis_lim > 0) launch_pdl(bpw_iter_kernel<DV, DC, true, false>, grid, block, st, pdl, p);
+    else launch_pdl(bpw_iter_kernel<DV, DC, false, false>, grid, block, st, pdl, p);
     if (sample) {
         cudaEventRecord(ev[1], st);
         cudaEventRecord(ev[2], st);                             // one kernel per iteration: the second interval is empty
@@ -547,6 +650,12 @@ int bp_launch_window_node_end(int dv, int dc, const BpParams &p, cudaStream_t st
     g_prof.launches += 1;
     bpw_window_end_kernel<<<grid, 32 * NS_WARPS, 0, st>>>(p);
     return 0;
+}
+
+void bp_launch_window_node_traj_init(const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    bpw_traj_init_kernel<<<p.G, 256, 0, st>>>(p);
 }
 
 // resume: the caller supplied both planes (scldpc_bp_window_range), only the list bookkeeping is reset

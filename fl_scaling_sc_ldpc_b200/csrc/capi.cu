@@ -29,6 +29,8 @@ void bp_launch_node_tables(const BpParams &p, cudaStream_t st);
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
 void bp_launch_window_node_init(const BpParams &p, cudaStream_t st, bool resume);
 int bp_launch_window_node_end(int dv, int dc, const BpParams &p, cudaStream_t st);
+void bp_launch_window_node_traj_init(const BpParams &p, cudaStream_t st);
+void bp_launch_pos_count_of(const BpParams &p, const u128 *plane, int *out, cudaStream_t st);
 void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st);
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st);
 int bp_launch_count_pairs(int dv, int dc, const BpParams &p, cudaStream_t st);
@@ -158,6 +160,17 @@ static size_t list_regions(size_t max_nodes, size_t ch)
     return blocks * NS_WARPS;
 }
 
+// entries per region: a warp makes `trips` trips of 32 (node, chunk) items per sweep and logs about 0.5 resolutions per item
+// in steady state (more in the first iterations of a frame); 48 per trip, rounded up to a power of two, 1024 .. 16384
+static size_t list_stride(size_t max_nodes, size_t ch)
+{
+    const size_t regions = list_regions(max_nodes, ch);
+    const size_t trips = (max_nodes * ch + regions * 32 - 1) / (regions * 32);
+    size_t s = NS_WCAP;
+    while (s < 48 * trips && s < 16384) s <<= 1;
+    return s;
+}
+
 static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *p)
 {
     const size_t G = d->n_graphs, W = d->n_words, ch = W / 2, lanes = 64 * W;
@@ -207,24 +220,26 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         if (no_msgs) {
             const size_t RW = list_regions(nk, ch);
             q.nl_rw = (int)RW;
-            q.nl_cap = env_int("SCLDPC_LIST_CAP", NS_WCAP, 1, NS_WCAP);   // test hook: does not change the layout
+            q.nl_stride = (int)list_stride(nk, ch);
+            q.nl_cap = env_int("SCLDPC_LIST_CAP", q.nl_stride, 1, q.nl_stride);   // test hook: does not change the layout
             q.noprog = c.take<u64>(G * W);
             q.cn_row = c.take<int32_t>(G * nk * d->dc);
-            q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
+            q.nl_list = c.take<uint2>(G * 2 * RW * (size_t)q.nl_stride);
             q.nl_cnt = c.take<int>(G * 2 * RW);
             q.nl_ovf = c.take<int>(G * 2);
         }
     }
     q.cn_dis = (flags & SCLDPC_F_STREAM) ? nullptr : c.take<u128>(G * nk * ch);   // sized for the largest possible ignored head
-    if (!(flags & (SCLDPC_F_STREAM | SCLDPC_F_MESSAGES | SCLDPC_F_TRAJECTORY))) {
+    if (!(flags & (SCLDPC_F_STREAM | SCLDPC_F_MESSAGES))) {
         // node-state window decoder / synchronous full BP (bp_window_node_kernels.cu): per-warp resolution lists
         const size_t RW = list_regions(nk > n / 4 ? nk : n / 4, ch);
         q.nl_rw = (int)RW;
-        q.nl_cap = env_int("SCLDPC_LIST_CAP", NS_WCAP, 1, NS_WCAP);
+        q.nl_stride = (int)list_stride(nk > n / 4 ? nk : n / 4, ch);
+        q.nl_cap = env_int("SCLDPC_LIST_CAP", q.nl_stride, 1, q.nl_stride);
         q.noprog = c.take<u64>(G * W);
         q.win_known = c.take<u64>(G * W);
         q.nl_last = c.take<int>(G);
-        q.nl_list = c.take<uint2>(G * 2 * RW * NS_WCAP);
+        q.nl_list = c.take<uint2>(G * 2 * RW * (size_t)q.nl_stride);
         q.nl_cnt = c.take<int>(G * 2 * RW);
         q.nl_ovf = c.take<int>(G * 2);
     }
@@ -521,15 +536,25 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool traj = flags & SCLDPC_F_TRAJECTORY, term = flags & SCLDPC_F_TERMINATED;
     const int cap = max_it <= 0 ? INT_MAX : max_it;
-    // Error-rate runs (no trajectory) decode in node-state form: the window kernels of bp_kernels.cu with
-    // one window that covers the whole code -- same erased set and stopping at every iteration as the message kernels,
-    // which SCLDPC_FULL_NODE=0 selects and which trajectory mode always uses.
-    const bool node = !traj && d->n_frames > 0 && !(flags & SCLDPC_F_MESSAGES);
+    // Node-state form (bp_window_node_kernels.cu) unless SCLDPC_F_MESSAGES asks for explicit messages: one window that
+    // covers the whole code -- same erased set and stopping at every iteration as the message kernels; with
+    // SCLDPC_F_TRAJECTORY the TRAJ variant, which also keeps the degree-one latch and exact per-position erasure counts.
+    // Trajectory rows from the node-state sweep pay up to M of a few 10^4 (48 100 against 27 500 frames/s at M = 10^4, cap 175);
+    // at M = 10^5 the per-(position, frame) counters see ten times the decrements on the same addresses and the message
+    // kernels win (3980 against 3000 frames/s), so very large codes keep them unless SCLDPC_F_NODE_TRAJ insists.
+    const bool node = d->n_frames > 0 && !(flags & SCLDPC_F_MESSAGES) &&
+                      (!traj || d->vns_pos <= 32768 || (flags & SCLDPC_F_NODE_TRAJ));
     if (node) {
         p.xb = p.y;
         p.win_lists = 1;                         // the sweep covers the whole chain: few rows change per iteration
+        p.traj_node = traj ? 1 : 0;
         bp_launch_init_ctrl_only(p, d->n_frames, st);
         bp_launch_window_node_init(p, st, false);
+        if (traj) {
+            CU(cudaMemsetAsync(p.latch, 0, sizeof(u128) * (size_t)p.G * p.nk * p.chunks, st));
+            bp_launch_window_node_traj_init(p, st);
+            bp_launch_pos_count_of(p, p.chan, p.pos_pairs, st);          // erased VNs per (position, frame) to start with
+        }
     } else bp_launch_init(p, d->dv, d->dc, traj, d->n_frames, st);
     CU(cudaGetLastError());
     p.c0 = 0;
@@ -548,6 +573,7 @@ extern "C" int scldpc_bp_full(const scldpc_dims_t *d, const scldpc_batch_t *b, i
     if (wave) bp_launch_wave_init(p, st);
     if (d->n_frames > 0 && (rc = run_iterations(&p, d->dv, d->dc, cap, traj, false, wave, st, &launched, node))) return rc;
     if (node && bp_launch_window_node_end(d->dv, d->dc, p, st)) return fail(SCLDPC_EINVAL, "unsupported degrees");
+    if (node && traj) CU(cudaMemsetAsync(p.pos_pairs, 0, sizeof(int) * (size_t)p.G * p.L * p.lanes, st));   // back to its role in the finalisation
     BpFinalOut fo{out->residual_dev, out->blocks_err_dev, out->erasures_exp_dev, out->blocks_err_exp_dev, out->erasures_p1_dev,
                   (flags & SCLDPC_F_EXP_ALL) ? 1 : 0, 1, 0};
     if (d->n_frames == 0) CU(cudaMemsetAsync(out->erased_dev, 0, sizeof(u64) * (size_t)p.G * p.n * p.W, st));

@@ -15,7 +15,8 @@ typedef ulonglong2 u128;   // one 16-byte chunk = 128 bit-sliced frames
 // node-state frame streams (bp_node_kernels.cu): geometry of the per-warp resolution lists
 #define NS_WARPS 8            // warps per block of the sweep
 #define NS_MAX_BLOCKS 640     // blocks per graph of the sweep (>= 4 resident blocks x 148 SMs)
-#define NS_WCAP 1024          // list entries per warp and iteration; beyond that the iteration is caught up by a full pass
+#define NS_WCAP 1024          // least list entries per warp and iteration (capi.cu sizes the regions by the trips a warp makes);
+                              // a region that overflows has its iteration caught up by a full pass
 
 __device__ __forceinline__ u128 make_u128(u64 a, u64 b) { u128 r; r.x = a; r.y = b; return r; }
 __device__ __forceinline__ u128 operator|(u128 a, u128 b) { return make_u128(a.x | b.x, a.y | b.y); }
@@ -253,14 +254,17 @@ struct BpParams {
     u64 *noprog;              // [G][W] node-state streams: lanes that stopped because an iteration resolved nothing (see bp_node_kernels.cu)
     int32_t *cn_row;          // [G][nk][dc] node-state streams: x-plane row offset (v << chunk_shift) of each CN edge; absent edges
                               //   point at the all-zero row behind the last graph's plane
-    uint2 *nl_list;           // [G][2][nl_rw][NS_WCAP] node-state sweeps: (32-bit word of the plane, bits cleared) per
+    uint2 *nl_list;           // [G][2][nl_rw][nl_stride] node-state sweeps: (32-bit word of the plane, bits cleared) per
                               //   resolution of the previous iteration, one private region per warp of the sweep's grid
     int *nl_cnt;              // [G][2][nl_rw] entries in each region
-    int nl_cap;               // entries of a region in use (NS_WCAP; SCLDPC_LIST_CAP lowers it so that tests reach the overflow path)
+    int nl_stride;            // entries per region: about 48 per trip of a warp (1.5 per thread and trip; measured ~0.5), at least NS_WCAP
+    int nl_cap;               // entries of a region in use (nl_stride; SCLDPC_LIST_CAP lowers it so that tests reach the overflow path)
     int nl_rw;                // regions per graph and parity: 8 warps x blocks of the largest sweep, at most NS_MAX_BLOCKS*NS_WARPS
     int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
     int *nl_last;             // [G] node-state window decoder: last iteration the graph executed in the current window
     u64 *win_known;           // [G][W] node-state window decoder: lanes in which the channel left some VN known
+    int traj_node;            // node-state synchronous full BP with trajectory rows (bpw_iter_kernel<.,.,.,TRAJ>): pos_pairs holds the
+                              //   erased VNs per (position, lane) while decoding, cnt_dvn slot 0 NumErasuresPrec, cnt_deg1 the deg-1 counts
     int win_lists;            // node-state window decoder: 1 = resolution lists (one launch per iteration, bp_window_node_kernels.cu),
                               //   0 = copy variant (CN sweep + copy of the VN window)
     int lazy_success;         // 1: "no erased VN is left" is not tracked per iteration; a frame that finishes stops one iteration
@@ -297,7 +301,7 @@ __device__ __forceinline__ void ns_replay_region(const BpParams &p, int g, int p
     const int RW = p.nl_rw;
     int *cntp = p.nl_cnt + (size_t)(g * 2 + par_prev) * RW + rid;
     const int cnt = ld_cg(cntp);
-    const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * NS_WCAP;
+    const uint2 *reg = p.nl_list + ((size_t)(g * 2 + par_prev) * RW + rid) * p.nl_stride;
     // eight independent loads in flight per thread (a region holds ~200 entries): one L2 round trip instead of seven
     constexpr int U = 8;
     for (int i0 = threadIdx.x & 31; i0 < cnt; i0 += 32 * U) {

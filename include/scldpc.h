@@ -41,7 +41,8 @@ extern "C" {
 
 /* decoder flags */
 #define SCLDPC_F_TERMINATED 1u   /* is_term (BP_TRAJ.c:901): 0 = truncated, tail CNs always send erasures      */
-#define SCLDPC_F_TRAJECTORY 2u   /* record (deg_1_iter, dVNs, first erased position) per iteration              */
+#define SCLDPC_F_TRAJECTORY 2u   /* record (deg_1_iter, dVNs, first erased position) per iteration (node-state sweep with a CN
+                                    latch and per-position counters, or the message kernels with SCLDPC_F_MESSAGES)          */
 #define SCLDPC_F_SQUARE 4u       /* window decoder: square window (BP_SW.c) instead of classical (BP_FULL.c)    */
 #define SCLDPC_F_EXP_ALL 8u      /* expurgated statistics over all positions (decodeBP_SW) instead of the first */
 #define SCLDPC_F_STREAM 32u      /* internal: workspace sizing of scldpc_bp_stream */
@@ -50,6 +51,7 @@ extern "C" {
                                     sweeps, which yield the same erased set at every iteration.  Applies
                                     to scldpc_bp_full without a trajectory, scldpc_bp_window and scldpc_bp_stream; workspace
                                     sizes depend on it, so pass the same flags to the *_workspace_bytes query and the call  */
+#define SCLDPC_F_NODE_TRAJ 256u  /* scldpc_bp_full with SCLDPC_F_TRAJECTORY: node-state sweep even above 32768 VNs per position   */
 #define SCLDPC_F_NO_WAVE 128u    /* scldpc_bp_full with messages: sweep every position in every iteration (testing)          */
 
 typedef struct {

@@ -40,8 +40,13 @@ def test_peeling_prefix_at_M_1e5_matches_oracle(big):
         assert int(rec[0, f]) == o_rec == steps
 
 
-def test_bp_trajectory_at_M_1e5_matches_oracle_and_moments(big):
+@pytest.mark.parametrize("force_node", [False, True])
+def test_bp_trajectory_at_M_1e5_matches_oracle_and_moments(big, force_node, monkeypatch):
+    """default at this size: message kernels; with SCLDPC_F_NODE_TRAJ the node-state sweep with its latch and counters"""
     ens, fb, g = big
+    if force_node:
+        from fl_scaling_sc_ldpc_b200 import _lib
+        monkeypatch.setattr(eng.engine, "F_TRAJECTORY", _lib.F_TRAJECTORY | _lib.F_NODE_TRAJ)
     fb.generate_erasures(0.40, 518, doping_points=DOPED)
     cap = 400
     res, erased, rows, _ = eng.decode_bp_full(fb, cap, True, trajectory=True, max_rows=cap, collect=False)
