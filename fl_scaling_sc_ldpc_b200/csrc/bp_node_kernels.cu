@@ -265,50 +265,86 @@ __global__ void ns_settle_done_kernel(BpParams p)
 
 // After a harvest: the freed lanes take their new frames.  The erased set starts as the channel's (Lji = channel value on
 // every edge, BP_FULL.c:913-917), written to both planes; the lanes iterate from the next launch on.
+//
+// The harvest hands out consecutive frame ids in ascending lane order, so the armed lanes of a graph are one run of frame ids
+// [f0, f0+A) and one Philox call -- four frames of one VN -- serves four armed lanes wherever they sit in the row.  A block takes
+// tiles of ARM_ROWS VN rows: phase 1 spreads (row, Philox block) pairs over the threads and ORs the erased frames into a shared
+// copy of the rows' armed bits (exactly ceil(A/4) calls per VN, against one call per armed lane and 128-lane chunk when every
+// thread drew the lanes of its own chunk: the kernel was 7.8 % of the benchmarked step, profiles/r02e); phase 2 merges the tile
+// into both planes with coalesced 16-byte accesses.
+#define ARM_ROWS 128
 __global__ void __launch_bounds__(256, 4) ns_arm_kernel(BpParams p)
 {
     const int g = blockIdx.y;
     if (ld_cg(p.alive + g) == 0) return;
-    __shared__ u64 s_first[SCLDPC_MAX_WORDS];
-    if (threadIdx.x < SCLDPC_MAX_WORDS) s_first[threadIdx.x] = 0;
+    __shared__ u64 s_first[SCLDPC_MAX_WORDS], s_armw[SCLDPC_MAX_WORDS];
+    __shared__ int s_rank[SCLDPC_MAX_WORDS + 1];
+    __shared__ unsigned short s_lane[SCLDPC_MAX_LANES];
+    __shared__ unsigned s_bits[ARM_ROWS * 2 * SCLDPC_MAX_WORDS];
+    const int W = p.W, ch = p.chunks, RWORDS = 2 * W;           // 32-bit words per plane row
+    if (threadIdx.x < SCLDPC_MAX_WORDS) {
+        s_first[threadIdx.x] = 0;
+        s_armw[threadIdx.x] = threadIdx.x < W ? p.arm_mask[g * W + threadIdx.x] : 0ull;
+    }
     __syncthreads();
-    const int ch = p.chunks;
+    if (threadIdx.x == 0) {
+        int r = 0;
+        for (int w = 0; w < W; w++) { s_rank[w] = r; r += __popcll(s_armw[w]); }
+        s_rank[W] = r;
+    }
+    __syncthreads();
+    const int A = s_rank[W];
+    if (A == 0) return;
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_armw[w] >> b) & 1ull) s_lane[s_rank[w] + __popcll(s_armw[w] & ((1ull << b) - 1ull))] = (unsigned short)l;
+    }
+    __syncthreads();
+    const uint32_t f0 = (uint32_t)p.lane_frame[g * p.lanes + s_lane[0]];
+    const uint32_t blk0 = f0 >> 2;
+    const int nb = (int)(((f0 + (uint32_t)A - 1u) >> 2) - blk0) + 1;
     const int k = threadIdx.x & (ch - 1);
-    const u128 arm = reinterpret_cast<const u128 *>(p.arm_mask)[g * ch + k];
+    const u128 arm = make_u128(s_armw[2 * k], s_armw[2 * k + 1]);
     u128 acc_first = zero128();
     u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
     u128 *__restrict__ xb = p.xb + (size_t)g * p.n * ch;
-    const int items = p.n << p.chunk_shift;
     const u64 thr = p.thr[g];
     const uint64_t gid = p.first_graph + (uint64_t)g;
-    if (nz(arm))
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < items; idx += gridDim.x * blockDim.x) {
-            const int v = idx >> p.chunk_shift;
-            const bool forced = p.known && (v % p.vns_pos) < p.known[v / p.vns_pos];
-            u128 cw = zero128();
-            // freed lanes get consecutive frame ids in ascending lane order, so one Philox call (4 frames) is
-            // usually shared by up to four armed lanes
-            uint32_t blk = 0xffffffffu, r4[4] = {0, 0, 0, 0};
-            for (int half = 0; half < 2; half++) {
-                u64 m = half ? arm.y : arm.x, w = 0;
-                while (m && !forced) {
-                    const int b = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const uint32_t fr = (uint32_t)p.lane_frame[g * p.lanes + k * 128 + half * 64 + b];
-                    if ((fr >> 2) != blk) {
-                        blk = fr >> 2;
-                        philox4x32_10((uint32_t)v, blk, (uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)p.seed ^ 0x6368616Eu,
-                                      (uint32_t)(p.seed >> 32), r4);
-                    }
-                    if ((u64)r4[fr & 3] < thr) w |= 1ull << b;
+    const uint32_t k0 = (uint32_t)p.seed ^ 0x6368616Eu, k1 = (uint32_t)(p.seed >> 32);
+    for (int row0 = blockIdx.x * ARM_ROWS; row0 < p.n; row0 += gridDim.x * ARM_ROWS) {
+        const int rows = min(ARM_ROWS, p.n - row0);
+        for (int i = threadIdx.x; i < rows * RWORDS; i += blockDim.x) s_bits[i] = 0u;
+        __syncthreads();
+        // phase 1: channel draws, one Philox call per (VN, block of four frame ids)
+        for (int item = threadIdx.x; item < rows * nb; item += blockDim.x) {
+            const int vl = item / nb, j = item - vl * nb;
+            const int v = row0 + vl;
+            if (p.known && (v % p.vns_pos) < p.known[v / p.vns_pos]) continue;     // doped: known whatever the channel says
+            uint32_t r4[4];
+            philox4x32_10((uint32_t)v, blk0 + (uint32_t)j, (uint32_t)gid, (uint32_t)(gid >> 32), k0, k1, r4);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int i = (int)(4u * (blk0 + (uint32_t)j) + (uint32_t)s - f0);
+                if (i >= 0 && i < A && (u64)r4[s] < thr) {
+                    const int l = s_lane[i];
+                    atomicOr(&s_bits[vl * RWORDS + (l >> 5)], 1u << (l & 31));
                 }
-                if (half) cw.y = w; else cw.x = w;
             }
-            const u128 xo = x[idx];
-            const u128 xn = sel(arm, cw, xo);
-            if (neq(xn, xo)) { x[idx] = xn; xb[idx] = xn; }
-            acc_first |= ~cw & arm;
         }
+        __syncthreads();
+        // phase 2: the armed lanes of both planes take the new frames' channel bits
+        if (nz(arm))
+            for (int i = threadIdx.x; i < rows << p.chunk_shift; i += blockDim.x) {   // i % ch == k: blockDim is a multiple of ch
+                const unsigned *sb = s_bits + (i >> p.chunk_shift) * RWORDS + 4 * k;
+                const u128 cw = make_u128((u64)sb[0] | ((u64)sb[1] << 32), (u64)sb[2] | ((u64)sb[3] << 32));
+                const size_t idx = ((size_t)row0 << p.chunk_shift) + i;
+                const u128 xo = x[idx];
+                const u128 xn = sel(arm, cw, xo);
+                if (neq(xn, xo)) { x[idx] = xn; xb[idx] = xn; }
+                acc_first |= ~cw & arm;
+            }
+        __syncthreads();
+    }
     acc_first = warp_or_same_chunk(acc_first, ch);
     if ((threadIdx.x & 31) < ch) {
         if (acc_first.x) atomicOr(&s_first[2 * k], acc_first.x);
@@ -417,7 +453,7 @@ void bp_launch_node_arm(const BpParams &p, cudaStream_t st)
 {
     static int res = 0;
     if (!res) res = resident_blocks_ns(ns_arm_kernel, 256);
-    long long need = (((long long)p.n << p.chunk_shift) + 255) / 256;
+    long long need = ((long long)p.n + ARM_ROWS - 1) / ARM_ROWS;
     long long gx = need < res ? need : res;
     g_prof.launches += 1;
     ns_arm_kernel<<<dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G), 256, 0, st>>>(p);
