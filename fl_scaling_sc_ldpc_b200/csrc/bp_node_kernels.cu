@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     __shared__ int s_last;
     if (threadIdx.x < SCLDPC_MAX_WORDS) s_new[threadIdx.x] = 0;
     __syncthreads();
-    const int ch = p.chunks;
-    const int k = threadIdx.x & (ch - 1);
+    const int ch = p.chunks;                                    // row stride of the planes
+    // chunks the graph's live frames occupy: all of them until the tail of the stream, where the lane compaction (below) moves
+    // the frames still decoding into the lowest chunks and the sweep spreads its threads over those chunks only
+    const int cs = ld_cg(p.gshift + g), chn = 1 << cs;
+    const int k = threadIdx.x & (chn - 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = p.iter & 1;
     const size_t plane = (size_t)g * p.n * ch;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     const u128 *__restrict__ rdk = rd + k;
     const int32_t *__restrict__ cn_row = p.cn_row + (size_t)g * p.nk * DC;
     uint2 *__restrict__ reg = p.nl_list + ((size_t)(g * 2 + par) * RW + rid) * p.nl_stride;
-    const int items = p.c1 << p.chunk_shift;                    // CNs >= c1 (tail of a truncated code) are never swept
+    const int items = p.c1 << cs;                               // CNs >= c1 (tail of a truncated code) are never swept
     const int stride = gridDim.x * blockDim.x;
     int wcount = 0;                                             // entries this warp has logged (warp-uniform)
     u128 acc_new = zero128();
@@ -101,18 +104,18 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
     int e[DC];
     {
         const int idx0 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (NS_PREFETCH && lane_work && idx0 < items) load_row<DC>(cn_row + (size_t)(idx0 >> p.chunk_shift) * DC, e);
+        if (NS_PREFETCH && lane_work && idx0 < items) load_row<DC>(cn_row + (size_t)(idx0 >> cs) * DC, e);
     }
     for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < items; base += stride) {
         const int idx = base + lane;
         u128 res = zero128(), b0 = zero128(), b1 = zero128(), b2 = zero128(), b3 = zero128();
-        const int32_t *row = cn_row + (size_t)(idx >> p.chunk_shift) * DC;
+        const int32_t *row = cn_row + (size_t)(idx >> cs) * DC;
         if (lane_work && idx < items) {
             if (!NS_PREFETCH) load_row<DC>(row, e);
             u128 in[DC];
 #pragma unroll
             for (int j = 0; j < DC; j++) in[j] = (NS_VARIANT & 1) ? ld_cg128(rdk + (unsigned)e[j]) : ld_stream(rdk + (unsigned)e[j]);
-            if (NS_PREFETCH && idx + stride < items) load_row<DC>(row + (size_t)(stride >> p.chunk_shift) * DC, e);
+            if (NS_PREFETCH && idx + stride < items) load_row<DC>(row + (size_t)(stride >> cs) * DC, e);
             // saturating count of erased neighbours (one / two planes) and, in bit planes b0..b3, the index j of an erased
             // neighbour -- exact where it is needed, i.e. in the frames with exactly one
             u128 one = zero128(), tw = zero128();
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
             res = one & ~tw;                                    // frames in which exactly one neighbour of c is erased
             if (CAPPED) res &= act;
 #if NS_VARIANT & 16
-            if (nz(res)) reinterpret_cast<int *>(p.pos_er)[((size_t)g * (p.L + DV - 1) + (idx >> p.chunk_shift) / p.cns_pos) * ch + k] = p.iter + 1;
+            if (nz(res)) reinterpret_cast<int *>(p.pos_er)[((size_t)g * (p.L + DV - 1) + (idx >> cs) / p.cns_pos) * ch + k] = p.iter + 1;
 #endif
         }
         if (__ballot_sync(0xffffffffu, nz(res)) == 0u) continue;
@@ -171,8 +174,8 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
         p.nl_cnt[(size_t)(g * 2 + par) * RW + rid] = wcount < p.nl_cap ? wcount : p.nl_cap;
         if (wcount > p.nl_cap) p.nl_ovf[g * 2 + par] = 1;
     }
-    acc_new = warp_or_same_chunk(acc_new, ch);
-    if (lane < ch) {
+    acc_new = warp_or_same_chunk(acc_new, chn);
+    if (lane < chn) {
         if (acc_new.x) atomicOr(&s_new[2 * k], acc_new.x);
         if (acc_new.y) atomicOr(&s_new[2 * k + 1], acc_new.y);
     }
@@ -357,6 +360,104 @@ __global__ void __launch_bounds__(256, 4) ns_arm_kernel(BpParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// lane compaction in the tail of a stream
+// ------------------------------------------------------------------------------------------------------------
+// Once a graph has handed out its last frame, lanes only fall idle: the sweep keeps paying for every 128-lane chunk that
+// still holds one live frame, and the slowest frames (the ones that stall, twice the iterations of the others) are spread
+// over all chunks -- about 1000 of the 14 500 iterations of the benchmarked eps = 0.49 graph run with a few dozen live frames
+// at the full price.  After a harvest that armed nothing, when the live frames fit into half the chunks in use, they move to
+// the lowest lanes: a frame's whole decoder state is its bit column in the (equal, settled) planes plus lane_frame and
+// lane_iter, so the move is one pass over the plane; gshift[g] then tells ns_iter_kernel to spread its threads over the
+// occupied chunks only.  Frame results are stored under the frame id, so nothing downstream sees the lane change.
+__global__ void ns_compact_plan_kernel(BpParams p)
+{
+    const int g = blockIdx.x, W = p.W;
+    __shared__ u64 s_act[SCLDPC_MAX_WORDS];
+    __shared__ int s_rank[SCLDPC_MAX_WORDS + 1], s_go;
+    __shared__ int s_fr[SCLDPC_MAX_LANES], s_it[SCLDPC_MAX_LANES];
+    if (threadIdx.x == 0) {
+        p.cmp_cnt[g] = 0;
+        int go = ld_cg(p.alive + g) != 0 && p.next_frame[g] >= p.frames_per_graph && p.gshift[g] > 0;
+        int r = 0;
+        for (int w = 0; w < W; w++) {
+            s_act[w] = p.active[g * W + w];
+            if (p.arm_mask[g * W + w] | p.done_mask[g * W + w]) go = 0;
+            s_rank[w] = r;
+            r += __popcll(s_act[w]);
+        }
+        s_rank[W] = r;
+        if (go && (r < 1 || r > (64 << p.gshift[g]))) go = 0;    // worth it when the live frames fit into half the chunks in use
+        s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const int A = s_rank[W];
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        const int w = l >> 6, b = l & 63;
+        if ((s_act[w] >> b) & 1ull) {
+            const int i = s_rank[w] + __popcll(s_act[w] & ((1ull << b) - 1ull));
+            p.cmp_src[g * p.lanes + i] = l;
+            s_fr[i] = p.lane_frame[g * p.lanes + l];
+            s_it[i] = p.lane_iter[g * p.lanes + l];
+        }
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < p.lanes; l += blockDim.x) {
+        p.lane_frame[g * p.lanes + l] = l < A ? s_fr[l] : -1;
+        p.lane_iter[g * p.lanes + l] = l < A ? s_it[l] : 0;
+    }
+    for (int w = threadIdx.x; w < W; w += blockDim.x)
+        p.active[g * W + w] = A >= 64 * (w + 1) ? ~0ull : (A <= 64 * w ? 0ull : ((1ull << (A - 64 * w)) - 1ull));
+    if (threadIdx.x == 0) {
+        int s = 0;
+        while ((128 << s) < A) s++;
+        p.gshift[g] = s;
+        p.cmp_cnt[g] = A;
+    }
+}
+
+#define CMP_ROWS 64
+__global__ void __launch_bounds__(256) ns_compact_kernel(BpParams p)
+{
+    const int g = blockIdx.y;
+    const int A = ld_cg(p.cmp_cnt + g);
+    if (A == 0) return;
+    __shared__ unsigned short s_src[SCLDPC_MAX_LANES];
+    __shared__ u128 s_in[CMP_ROWS * SCLDPC_MAX_WORDS / 2], s_out[CMP_ROWS * SCLDPC_MAX_WORDS / 2];
+    const int ch = p.chunks, RWORDS = 2 * p.W, AW = (A + 31) >> 5;
+    for (int i = threadIdx.x; i < A; i += blockDim.x) s_src[i] = (unsigned short)p.cmp_src[g * p.lanes + i];
+    u128 *__restrict__ x = p.x + (size_t)g * p.n * ch;
+    u128 *__restrict__ xb = p.xb + (size_t)g * p.n * ch;
+    const unsigned *in32 = reinterpret_cast<const unsigned *>(s_in);
+    unsigned *out32 = reinterpret_cast<unsigned *>(s_out);
+    for (int row0 = blockIdx.x * CMP_ROWS; row0 < p.n; row0 += gridDim.x * CMP_ROWS) {
+        const int rows = min(CMP_ROWS, p.n - row0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * ch; i += blockDim.x) {
+            s_in[i] = x[(size_t)row0 * ch + i];
+            s_out[i] = zero128();
+        }
+        __syncthreads();
+        for (int item = threadIdx.x; item < rows * AW; item += blockDim.x) {
+            const int r = item / AW, q = item - r * AW;
+            const unsigned *src = in32 + r * RWORDS;
+            unsigned o = 0;
+            const int nbits = min(32, A - 32 * q);
+            for (int b = 0; b < nbits; b++) {
+                const int l = s_src[32 * q + b];
+                o |= ((src[l >> 5] >> (l & 31)) & 1u) << b;
+            }
+            out32[r * RWORDS + q] = o;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * ch; i += blockDim.x) {
+            const u128 v = s_out[i];
+            if (neq(v, s_in[i])) { x[(size_t)row0 * ch + i] = v; xb[(size_t)row0 * ch + i] = v; }
+        }
+    }
+}
+
 // x-plane row offsets of the CN edges (once per stream call)
 __global__ void ns_cn_row_kernel(BpParams p)
 {
@@ -366,6 +467,7 @@ __global__ void ns_cn_row_kernel(BpParams p)
     int32_t *cn_row = p.cn_row + (size_t)g * items;
     // absent edges read the all-zero row that follows the last graph's plane
     const unsigned zero_row = (unsigned)(((size_t)(p.G - g) * p.n) << p.chunk_shift);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.gshift[g] = p.chunk_shift; p.cmp_cnt[g] = 0; }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (size_t)gridDim.x * blockDim.x) {
         const int e = cn_edge[i];
         cn_row[i] = (e != p.E) ? (int32_t)((unsigned)(e / p.dv) << p.chunk_shift) : (int32_t)zero_row;
@@ -457,6 +559,14 @@ void bp_launch_node_arm(const BpParams &p, cudaStream_t st)
     long long gx = need < res ? need : res;
     g_prof.launches += 1;
     ns_arm_kernel<<<dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G), 256, 0, st>>>(p);
+}
+
+// after the harvest and the arming: graphs in the tail of their stream move their live frames into the lowest lanes
+void bp_launch_node_compact(const BpParams &p, cudaStream_t st)
+{
+    g_prof.launches += 2;
+    ns_compact_plan_kernel<<<p.G, 256, 0, st>>>(p);
+    ns_compact_kernel<<<dim3(592, (unsigned)p.G), 256, 0, st>>>(p);
 }
 
 void bp_launch_node_tables(const BpParams &p, cudaStream_t st)

@@ -25,6 +25,7 @@ int bp_launch_stream_iteration(int dv, int dc, const BpParams &p, bool arm, cuda
 int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool after_harvest, cudaStream_t st);
 void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st);
 void bp_launch_node_arm(const BpParams &p, cudaStream_t st);
+void bp_launch_node_compact(const BpParams &p, cudaStream_t st);
 void bp_launch_node_tables(const BpParams &p, cudaStream_t st);
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
 void bp_launch_window_node_init(const BpParams &p, cudaStream_t st, bool resume);
@@ -227,6 +228,9 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
             q.nl_list = c.take<uint2>(G * 2 * RW * (size_t)q.nl_stride);
             q.nl_cnt = c.take<int>(G * 2 * RW);
             q.nl_ovf = c.take<int>(G * 2);
+            q.gshift = c.take<int>(G);
+            q.cmp_cnt = c.take<int>(G);
+            q.cmp_src = c.take<int>(G * lanes);
         }
     }
     q.cn_dis = (flags & SCLDPC_F_STREAM) ? nullptr : c.take<u128>(G * nk * ch);   // sized for the largest possible ignored head
@@ -695,6 +699,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     // (profiles/r02h_harvest_period_ab.txt: 5.62 .. 5.82e13 edge-updates/s for constants 25 .. 60 and both policies).
     const int hc10 = env_int("SCLDPC_HARVEST_C10", 60, 1, 1000);
     const int h_policy_max = env_int("SCLDPC_HARVEST_POLICY", 0, 0, 1);
+    const bool compact = env_int("SCLDPC_COMPACT", 1, 0, 1) != 0;   // lane compaction in the tail of a stream (A/B switch)
     int H = adaptive ? 16 : cfg->harvest_every;
     CU(cudaMemsetAsync(p.alive_total + 1, 0, 2 * sizeof(int), st));
     CU(cudaMemsetAsync(p.alive_total + 4, 0x7f, 2 * sizeof(int), st));
@@ -719,6 +724,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         bp_launch_count_pairs(d->dv, d->dc, p, st);
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
         if (node) bp_launch_node_arm(p, st);
+        if (node && compact) bp_launch_node_compact(p, st);
         CU_LAUNCHES();
         CU(cudaMemcpyAsync(hf + 8 * slot, p.alive_total, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
@@ -863,7 +869,7 @@ extern "C" size_t scldpc_peel_workspace_bytes(const scldpc_dims_t *d, int n_cn_a
     if (check_dims(d) || have_device()) return 0;
     const int grid = peel_grid(total_size, (long long)d->n_graphs * d->n_frames, n_cn_all);
     if (grid < 0) { fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap"); return 0; }
-    return sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size);
+    return sizeof(u64) * ((size_t)grid * peel_state_words(n_cn_all, total_size) + 1);     // + the frame counter
 }
 
 extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *vn_cn_dev, const uint64_t *chan_dev, int n_cn_all,
@@ -880,13 +886,16 @@ extern "C" int scldpc_peel_trajectories(const scldpc_dims_t *d, const int32_t *v
     if (frames == 0) return 0;
     const int grid = peel_grid(total_size, frames, n_cn_all);
     if (grid < 0) return fail(SCLDPC_EINVAL, "total_size too large for the shared-memory bitmap");
-    if (workspace_bytes < sizeof(u64) * (size_t)grid * peel_state_words(n_cn_all, total_size)) return fail(SCLDPC_ENOMEM, "workspace too small");
+    const size_t st_words = (size_t)grid * peel_state_words(n_cn_all, total_size);
+    if (workspace_bytes < sizeof(u64) * (st_words + 1)) return fail(SCLDPC_ENOMEM, "workspace too small");
     PeelParams p;
     memset(&p, 0, sizeof p);
     p.n = d->L * d->vns_pos; p.dv = d->dv; p.n_cn_all = n_cn_all; p.total_size = total_size; p.num_steps = num_steps;
     p.W = d->n_words; p.n_frames = d->n_frames; p.G = d->n_graphs;
     p.vn_cn = vn_cn_dev; p.chan = reinterpret_cast<const u64 *>(chan_dev); p.state = static_cast<u64 *>(workspace_dev);
     p.r1 = r1_dev; p.recovered = recovered_dev; p.n_erased = n_erased_dev; p.seed = seed; p.first_frame = first_frame_id;
+    p.next = p.state + st_words;                 // frames are handed out dynamically once every warp has its first one
+    CU(cudaMemsetAsync(p.next, 0, sizeof(u64), static_cast<cudaStream_t>(stream)));
     if (peel_launch(p, grid, static_cast<cudaStream_t>(stream))) return fail(SCLDPC_EINVAL, "peeling launch configuration failed");
     CU(cudaGetLastError());
     return 0;

@@ -261,6 +261,10 @@ struct BpParams {
     int nl_cap;               // entries of a region in use (nl_stride; SCLDPC_LIST_CAP lowers it so that tests reach the overflow path)
     int nl_rw;                // regions per graph and parity: 8 warps x blocks of the largest sweep, at most NS_MAX_BLOCKS*NS_WARPS
     int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
+    int *gshift;              // [G] node-state streams: log2 of the 128-lane chunks the graph's live frames occupy (chunk_shift until the
+                              //   tail of the stream, then lowered by the lane compaction, bp_node_kernels.cu)
+    int *cmp_cnt;             // [G] lanes moved by the compaction planned at this harvest (0: none)
+    int *cmp_src;             // [G][lanes] compaction: lane i takes the frame of lane cmp_src[i]
     int *nl_last;             // [G] node-state window decoder: last iteration the graph executed in the current window
     u64 *win_known;           // [G][W] node-state window decoder: lanes in which the channel left some VN known
     int traj_node;            // node-state synchronous full BP with trajectory rows (bpw_iter_kernel<.,.,.,TRAJ>): pos_pairs holds the
@@ -402,6 +406,7 @@ struct PeelParams {
     const int32_t *vn_cn;          // [G][n][dv]
     const u64 *chan;               // [G][n][W]
     u64 *state;                    // [gridDim.x][n_cn_all]  (degree << 32) + id sum
+    u64 *next;                     // frames handed out beyond the first one of every warp
     int32_t *r1;                   // [G][n_frames][num_steps+1] or NULL
     int32_t *recovered;            // [G][n_frames]
     int32_t *n_erased;             // [G][n_frames]

@@ -61,29 +61,35 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 // one-warp blocks allow).  Dynamic shared memory per warp: [bitmap words |] level-1 counts | level-2 counts.  When a
 // warp's bitmap does not leave room for 64 frames per SM it lives in global memory behind the warp's CN state (it is touched
 // by a handful of words per step); the counts always stay in shared memory.
+// BITS_GLOBAL is a template parameter so that the bitmap's address space is static: through a generic pointer the bit updates
+// compiled to generic ATOM instead of ATOMS / RED.
 #define PEEL_WPB 2
+template <bool BITS_GLOBAL>
 __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelParams p)
 {
     extern __shared__ unsigned s_mem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * PEEL_WPB + warp, n_slots = gridDim.x * PEEL_WPB;
-    unsigned *s_mem = s_mem_all + (size_t)warp * ((p.bits_global ? 0 : p.n_words1) + p.n_l1 + p.n_l2);
-    const size_t st_words = (size_t)p.n_cn_all + (p.bits_global ? ((size_t)p.n_words1 + 1) / 2 : 0);   // u64 per warp
+    unsigned *s_mem = s_mem_all + (size_t)warp * ((BITS_GLOBAL ? 0 : p.n_words1) + p.n_l1 + p.n_l2);
+    const size_t st_words = (size_t)p.n_cn_all + (BITS_GLOBAL ? ((size_t)p.n_words1 + 1) / 2 : 0);   // u64 per warp
     u64 *st = p.state + (size_t)slot * st_words;
-    unsigned *bits = p.bits_global ? reinterpret_cast<unsigned *>(st + p.n_cn_all) : s_mem;
-    int *l1 = reinterpret_cast<int *>(s_mem + (p.bits_global ? 0 : p.n_words1));
+    unsigned *bits_g = reinterpret_cast<unsigned *>(st + p.n_cn_all);   // BITS_GLOBAL
+    unsigned *bits_s = s_mem;                                           // !BITS_GLOBAL
+    int *l1 = reinterpret_cast<int *>(s_mem + (BITS_GLOBAL ? 0 : p.n_words1));
     int *l2 = l1 + p.n_l1;
     const int l2q = (p.n_l2 + 31) / 32;                           // level-2 entries per lane
     const long long total_frames = (long long)p.G * p.n_frames;
 
-    for (long long fr = slot; fr < total_frames; fr += n_slots) {
+    // the first frame of a warp is its slot number; further frames come from a counter, so warps whose frames stall early (most do
+    // at eps = 0.48 without termination) take over work from the ones that peel to the end
+    for (long long fr = slot; fr < total_frames;) {
         const int g = (int)(fr / p.n_frames), f = (int)(fr % p.n_frames);
         const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * p.dv;
         const u64 *chan = p.chan + (size_t)g * p.n * p.W + (f >> 6);
         const int fb = f & 63;
         // ---- residual graph of the erased VNs (schedule, PD.py:750-757) ----
         for (int i = lane; i < p.n_cn_all; i += 32) st[i] = 0;
-        for (int i = lane; i < p.n_words1; i += 32) bits[i] = 0;
+        for (int i = lane; i < p.n_words1; i += 32) { if (BITS_GLOBAL) bits_g[i] = 0; else bits_s[i] = 0; }
         for (int i = lane; i < p.n_l1 + p.n_l2; i += 32) l1[i] = 0;
         __syncwarp();
         int n_er = 0;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
             const bool one = c < p.total_size && (__ldcg(reinterpret_cast<const unsigned long long *>(st + c)) >> 32) == 1ull;
             const unsigned m = __ballot_sync(0xffffffffu, one);
             if (lane == 0 && m) {
-                bits[w] = m;
+                if (BITS_GLOBAL) bits_g[w] = m; else bits_s[w] = m;
                 const int pc = __popc(m);
                 l1[w >> 5] += pc;
                 l2[w >> 10] += pc;
@@ -125,7 +131,9 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
             if ((step & 3) == 0)
                 philox_peel((uint32_t)(step >> 2), 0u, (uint32_t)fid, (uint32_t)(fid >> 32), (uint32_t)p.seed ^ 0x7065656Cu,
                             (uint32_t)(p.seed >> 32), rnd);
-            int k = (int)(rnd[step & 3] % (uint32_t)cnt1);
+            const int h = step & 3;                             // selects instead of a dynamic index: rnd stays in registers
+            const uint32_t draw = h == 0 ? rnd[0] : (h == 1 ? rnd[1] : (h == 2 ? rnd[2] : rnd[3]));
+            int k = (int)(draw % (uint32_t)cnt1);
             // ---- select the k-th set bit ----
             int a = 0;
             for (int q = 0; q < l2q; q++) a += (lane * l2q + q) < p.n_l2 ? l2[lane * l2q + q] : 0;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
             k -= __shfl_sync(0xffffffffu, inc - a, sel);
             const int b1 = b2 * 32 + sel;
             const int wi = b1 * 32 + lane;
-            const unsigned word = wi < p.n_words1 ? (p.bits_global ? __ldcg(bits + wi) : bits[wi]) : 0u;
+            const unsigned word = wi < p.n_words1 ? (BITS_GLOBAL ? __ldcg(bits_g + wi) : bits_s[wi]) : 0u;
             a = __popc(word);
             inc = warp_incl_scan(a, lane);
             bal = __ballot_sync(0xffffffffu, k < inc);
@@ -165,12 +173,12 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
                 const int deg_old = (int)(old >> 32);
                 if (c < p.total_size) {                          // CNs >= total_size are not seen by the decoder
                     if (deg_old == 2) {                          // becomes degree one
-                        atomicOr(&bits[c >> 5], 1u << (c & 31));
+                        if (BITS_GLOBAL) atomicOr(&bits_g[c >> 5], 1u << (c & 31)); else atomicOr(&bits_s[c >> 5], 1u << (c & 31));
                         atomicAdd(&l1[c >> 10], 1);
                         atomicAdd(&l2[c >> 15], 1);
                         delta = 1;
                     } else if (deg_old == 1) {                   // stops being degree one
-                        atomicAnd(&bits[c >> 5], ~(1u << (c & 31)));
+                        if (BITS_GLOBAL) atomicAnd(&bits_g[c >> 5], ~(1u << (c & 31))); else atomicAnd(&bits_s[c >> 5], ~(1u << (c & 31)));
                         atomicSub(&l1[c >> 10], 1);
                         atomicSub(&l2[c >> 15], 1);
                         delta = -1;
@@ -188,8 +196,9 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
         if (lane == 0) {
             p.recovered[fr] = recovered;
             p.n_erased[fr] = n_er;
+            fr = (long long)n_slots + (long long)atomicAdd(reinterpret_cast<unsigned long long *>(p.next), 1ull);
         }
-        __syncwarp();
+        fr = __shfl_sync(0xffffffffu, fr, 0);
     }
 }
 
@@ -248,14 +257,20 @@ int peel_grid(int total_size, long long total_frames, int n_cn_all)
     int n_l2 = 0;
     const size_t smem = peel_smem_bytes(total_size, nullptr, nullptr, &n_l2, nullptr);
     if (smem > (size_t)max_smem || n_l2 > 32 * 8) return -1;
-    long long per_sm = (long long)(max_smem) / (long long)(smem + 64);
-    if (per_sm > 64) per_sm = 64;
-    if (per_sm < 1) per_sm = 1;
+    // frames in flight per SM = the warps that are really resident (registers allow fewer than the 64 the shared memory is sized
+    // for): a grid beyond that runs as a second, mostly empty wave
+    int big = 0, occ = 0;
+    peel_smem_bytes(total_size, nullptr, nullptr, nullptr, &big);
+    auto kernel = big ? peel_trajectory_kernel<true> : peel_trajectory_kernel<false>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * PEEL_WPB));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * PEEL_WPB, smem * PEEL_WPB) != cudaSuccess || occ < 1) occ = 1;
+    long long per_sm = (long long)occ * PEEL_WPB;
     long long grid = per_sm * sms;
     // keep the CN-state workspace (8 B per CN and frame in flight) under 24 GB: M = 1e5 holds 21 MB per frame
     const long long by_mem = (24ll << 30) / (8ll * (long long)peel_state_words(n_cn_all, total_size));
     if (grid > by_mem) grid = by_mem;
     if (grid > total_frames) grid = total_frames;
+    if (const char *e = getenv("SCLDPC_PEEL_SLOTS")) { const long long cap = atoll(e); if (cap > 0 && grid > cap) grid = cap; }   // timing experiments
     grid = (grid + PEEL_WPB - 1) / PEEL_WPB * PEEL_WPB;          // whole blocks
     return (int)(grid < PEEL_WPB ? PEEL_WPB : grid);
 }
@@ -264,9 +279,10 @@ int peel_launch(PeelParams p, int grid, cudaStream_t st)
 {
     const size_t smem = peel_smem_bytes(p.total_size, &p.n_words1, &p.n_l1, &p.n_l2, &p.bits_global);
     if (p.n_l2 > 32 * 8) return -1;                              // more than 2^23 CNs: one more level would be needed
-    if (cudaFuncSetAttribute(peel_trajectory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * PEEL_WPB)) != cudaSuccess) return -2;
+    auto kernel = p.bits_global ? peel_trajectory_kernel<true> : peel_trajectory_kernel<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * PEEL_WPB)) != cudaSuccess) return -2;
     g_prof.launches += 1;
-    peel_trajectory_kernel<<<grid / PEEL_WPB, 32 * PEEL_WPB, smem * PEEL_WPB, st>>>(p);
+    kernel<<<grid / PEEL_WPB, 32 * PEEL_WPB, smem * PEEL_WPB, st>>>(p);
     return 0;
 }
 
