@@ -477,12 +477,13 @@ def side_workloads(args, dev, side_cpu):
     # ---- config 4: sliding window, L = 100, non-terminated (derived mode)
     if want is None or "window_L100" in want:
         ensw = eng.Ensemble(DV, DC, 100, M)
-        fb = eng.FrameBatch(ensw, 4, 1024, 16, device=dev)
+        GW = 8                                                   # W = 3 sweeps 3 CN positions per iteration: 4 graphs do not fill the GPU
+        fb = eng.FrameBatch(ensw, GW, 1024, 16, device=dev)
         fb.generate_graphs(seed=args.seed, first_graph_id=7 << 20)
         wl = {}
         for W, e in ((3, 0.30), (5, 0.40), (10, 0.45)):
             def step(i, W=W, e=e):
-                fb.generate_erasures(e, args.seed + 1, first_graph_id=(7 << 20) + 4 * (i + 2))
+                fb.generate_erasures(e, args.seed + 1, first_graph_id=(7 << 20) + GW * (i + 2))
                 res, erased, rows, _ = eng.decode_bp_window(fb, W, 8, 60, square=True, is_term=False, collect=False)
                 return res
             step(-1)
@@ -493,11 +494,11 @@ def side_workloads(args, dev, side_cpu):
             r = eng.decode_bp_window(fb, W, 8, 60, square=True, is_term=False)
             work = 2 * r.edge_updates
             ach = work * (B_ALG / (2 * E_EDGES)) / dt / 1e9
-            wl[f"W={W}"] = {"value": work / dt, "unit": "edge-updates/s", "frames_per_s": 2 * 4 * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
+            wl[f"W={W}"] = {"value": work / dt, "unit": "edge-updates/s", "frames_per_s": 2 * GW * 1024 / dt, "ms_per_step": 1e3 * dt / 2,
                             "eps": e, "frame_error_rate": float((r.residual > 0).mean()),
                             "undecoded_vn_fraction": float(r.residual.mean()) / (100 * M),     # non-terminated: the last positions stay erased
                             "gpu_launches": launches,
-                            "roofline": {"bound": "hbm", "kernel": "bpw_cn_node_kernel<4,8> + bpw_vn_node_kernel (window iterations)",
+                            "roofline": {"bound": "hbm", "kernel": "bpw_cn_copy_kernel<4,8,false> + bpw_vn_copy_kernel (window iterations)",
                                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                                          "traffic": (tj.get("window_node", {}) or {}).get(f"W{W}_dram_bytes_per_launch"),
                                          "avg_launch_ms": [float(cn_ms.mean()), float(vn_ms.mean())] if len(cn_ms) else None,
@@ -505,7 +506,7 @@ def side_workloads(args, dev, side_cpu):
                                          "algorithmic_bytes": "0.2656 B per useful edge update (= (4E+n)/8 per frame-iteration of the window's "
                                                               "edges, message formulation); the node-state sweeps move less, so frac can exceed 1"}}
         out["window_L100"] = {"config": "(4,8) SC-LDPC non-terminated (derived mode) L=100 M=10000, square window, 8 iterations per window, "
-                                        "60 for the first; 4 graphs x 1024 frames per step, channel generation inside the timed region",
+                                        f"60 for the first; {GW} graphs x 1024 frames per step, channel generation inside the timed region",
                               "windows": wl, "cpu_baseline": (side_cpu or {}).get("window_W5")}
         del fb
         torch.cuda.empty_cache()
@@ -670,7 +671,7 @@ def run_ours(args):
                 kname, tn = "ns_iter_kernel<4,8,false>", tj.get("node_state_r2", {})
                 kwhat = "one flooding iteration = one launch: replay of the previous iteration's resolution lists + CN sweep + lane retirement"
             else:
-                kname, tn = "bpw_cn_node_kernel<4,8> + bpw_vn_node_kernel", {}
+                kname, tn = "bpw_iter_kernel<4,8,false,false>", {}
                 kwhat = "one flooding iteration"
             it_t = cn_avg + vn_avg
             ach = fi_per_launch * B_ALG / it_t / 1e9

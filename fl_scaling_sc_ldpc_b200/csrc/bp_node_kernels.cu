@@ -414,6 +414,10 @@ __global__ void ns_compact_plan_kernel(BpParams p)
         while ((128 << s) < A) s++;
         p.gshift[g] = s;
         p.cmp_cnt[g] = A;
+#if !(NS_VARIANT & 16)
+        p.swept[2 * g] += 1;                                    // scldpc_bp_sweep_stats on a stream workspace: compactions, lanes moved
+        p.swept[2 * g + 1] += A;
+#endif
     }
 }
 

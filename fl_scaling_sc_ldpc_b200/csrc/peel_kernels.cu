@@ -46,6 +46,18 @@ void peel_picks_host(uint64_t seed, uint64_t frame_id, int n, uint32_t *out)
 }
 
 
+// position of the (k+1)-th set bit of w (0 <= k < popc(w)): binary search on popcounts (__fns is a bit-by-bit loop in libdevice)
+__device__ __forceinline__ int select_bit(unsigned w, int k)
+{
+    int r = 0, t;
+    t = __popc(w & 0xffffu); if (k >= t) { k -= t; r += 16; w >>= 16; }
+    t = __popc(w & 0xffu);   if (k >= t) { k -= t; r += 8;  w >>= 8; }
+    t = __popc(w & 0xfu);    if (k >= t) { k -= t; r += 4;  w >>= 4; }
+    t = __popc(w & 0x3u);    if (k >= t) { k -= t; r += 2;  w >>= 2; }
+    t = (int)(w & 1u);       if (k >= t) r += 1;
+    return r;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
 #pragma unroll
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
             sel = __ffs(bal) - 1;
             k -= __shfl_sync(0xffffffffu, inc - a, sel);
             const unsigned wsel = __shfl_sync(0xffffffffu, word, sel);
-            const int m = (b1 * 32 + sel) * 32 + (int)__fns(wsel, 0, k + 1);
+            const int m = (b1 * 32 + sel) * 32 + select_bit(wsel, k);
             // ---- remove its VN (PD.py:769-780) ----
             const int v = (int)(uint32_t)__ldcg(reinterpret_cast<const unsigned long long *>(st + m));
             recovered++;
@@ -185,9 +197,7 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
                     }
                 }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
-            cnt1 += delta;
+            cnt1 += __reduce_add_sync(0xffffffffu, delta);
             __syncwarp();
             if (r1 && lane == 0) r1[step + 1] = cnt1;             // PD.py:781
         }

@@ -271,7 +271,9 @@ int scldpc_allreduce_counters(void *nccl_comm, int64_t *counters_dev, int n_int6
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 /* kernels launched by the library since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
- * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change) */
+ * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change).  On the workspace
+ * of a node-state scldpc_bp_stream call (flags SCLDPC_F_STREAM): out[0] = lane compactions done in the tails of the
+ * graphs' streams, out[1] = frames they moved */
 long long scldpc_launch_count(int reset);
 /* Sampled CUDA-event timing of the two sweeps of every sample_every-th flooding iteration (on the launching
  * stream).  profile_end synchronises the device and returns per sample the iteration index and the CN / VN sweep

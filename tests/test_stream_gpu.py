@@ -180,3 +180,35 @@ def test_resolution_list_overflow_falls_back_to_a_full_pass(cap, monkeypatch, st
     for key in KEYS:
         assert (getattr(a, key) == getattr(b, key)).all() and (getattr(w, key) == getattr(w2, key)).all(), key
     assert bool((a.erased_words == b.erased_words).all()) and bool((w.erased_words == w2.erased_words).all())
+
+
+def _stream_compactions(fb):
+    """(compactions, frames moved) of the last node-state stream call on fb's workspace (scldpc_bp_sweep_stats)"""
+    import ctypes
+    from fl_scaling_sc_ldpc_b200 import _lib
+    st = (ctypes.c_longlong * 2)()
+    _lib.check(_lib.lib().scldpc_bp_sweep_stats(ctypes.byref(fb.dims), 32, ctypes.c_void_p(fb._ws.data_ptr()), st))   # SCLDPC_F_STREAM
+    return int(st[0]), int(st[1])
+
+
+@pytest.mark.parametrize("lanes,B,cap", [(1024, 1300, 0), (512, 512, 0), (256, 700, 9), (1024, 1024, 0)])
+def test_lane_compaction_in_the_tail_changes_nothing(lanes, B, cap, monkeypatch, stream_kernels):
+    """Once a graph has handed out its last frame the live frames move into the lowest 128-lane chunks (ns_compact_*): the
+    per-frame results must not depend on it, and it must really happen (several times: 8 -> 4 -> 2 -> 1 chunks)"""
+    if stream_kernels == "messages":
+        pytest.skip("the message-passing streams do not compact")
+    ens = eng.Ensemble(4, 8, 14, 48)
+    fbg = eng.FrameBatch(ens, 3, lanes).generate_graphs(41, first_graph_id=3)
+    eps = [0.44, 0.49, 0.52]                                     # the last one stalls: long-lived frames spread over all chunks
+    ref = sync_reference(fbg, ens, B, eps, 9, True, max_it=cap)
+    for H in (1, 4, 0):
+        monkeypatch.setenv("SCLDPC_COMPACT", "0")
+        a = eng.decode_bp_stream(fbg, B, eps, 9, first_graph_id=3, harvest_every=H, max_it=cap)
+        assert _stream_compactions(fbg) == (0, 0)
+        monkeypatch.setenv("SCLDPC_COMPACT", "1")
+        b = eng.decode_bp_stream(fbg, B, eps, 9, first_graph_id=3, harvest_every=H, max_it=cap)
+        n_cmp, moved = _stream_compactions(fbg)
+        for key in KEYS:
+            assert (getattr(a, key) == ref[key]).all() and (getattr(b, key) == ref[key]).all(), (H, key)
+        if H == 1 and cap == 0:                                  # every iteration is a chance to compact
+            assert n_cmp >= 3 and moved >= n_cmp, (n_cmp, moved)
