@@ -77,7 +77,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 // compiled to generic ATOM instead of ATOMS / RED.
 #define PEEL_WPB 2
 template <bool BITS_GLOBAL>
-__global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelParams p)
+__global__ void __launch_bounds__(32 * PEEL_WPB, 20) peel_trajectory_kernel(PeelParams p)
 {
     extern __shared__ unsigned s_mem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,12 +105,24 @@ __global__ void __launch_bounds__(32 * PEEL_WPB) peel_trajectory_kernel(PeelPara
         for (int i = lane; i < p.n_l1 + p.n_l2; i += 32) l1[i] = 0;
         __syncwarp();
         int n_er = 0;
-        for (int v0 = 0; v0 < p.n; v0 += 32) {
-            const int v = v0 + lane;
-            if (v < p.n && ((chan[(size_t)v * p.W] >> fb) & 1ull)) {
-                n_er++;
-                for (int i = 0; i < p.dv; i++)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(st + vn_cn[(size_t)v * p.dv + i]), (1ull << 32) + (u64)v);
+        // eight channel words in flight per lane: one warp walks the n VNs of its frame alone, so the loop is a chain of HBM round
+        // trips (the sampled stalls of the first wave were all here, profiles/r02y_peel_M10000_ncu.csv)
+        constexpr int SU = 8;
+        for (int v0 = 0; v0 < p.n; v0 += 32 * SU) {
+            u64 cw[SU];
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const int v = v0 + 32 * u + lane;
+                cw[u] = v < p.n ? __ldg(chan + (size_t)v * p.W) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < SU; u++) {
+                const int v = v0 + 32 * u + lane;
+                if ((cw[u] >> fb) & 1ull) {
+                    n_er++;
+                    for (int i = 0; i < p.dv; i++)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(st + vn_cn[(size_t)v * p.dv + i]), (1ull << 32) + (u64)v);
+                }
             }
         }
 #pragma unroll
