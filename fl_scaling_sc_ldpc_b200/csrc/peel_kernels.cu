@@ -76,8 +76,11 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 // BITS_GLOBAL is a template parameter so that the bitmap's address space is static: through a generic pointer the bit updates
 // compiled to generic ATOM instead of ATOMS / RED.
 #define PEEL_WPB 2
+// Register targets (measured, profiles/r02z_peel_register_ab.txt): with the bitmap in shared memory (M = 1000) 47 registers / 42
+// warps per SM are best (the kernel is close to issue-bound there); with the bitmap in global memory (M >= 10000) the chain of HBM
+// round trips wants every warp the SM can hold: 32 registers / 64 warps, +10 %.
 template <bool BITS_GLOBAL>
-__global__ void __launch_bounds__(32 * PEEL_WPB, 20) peel_trajectory_kernel(PeelParams p)
+__global__ void __launch_bounds__(32 * PEEL_WPB, BITS_GLOBAL ? 28 : 20) peel_trajectory_kernel(PeelParams p)
 {
     extern __shared__ unsigned s_mem_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,24 +108,13 @@ __global__ void __launch_bounds__(32 * PEEL_WPB, 20) peel_trajectory_kernel(Peel
         for (int i = lane; i < p.n_l1 + p.n_l2; i += 32) l1[i] = 0;
         __syncwarp();
         int n_er = 0;
-        // eight channel words in flight per lane: one warp walks the n VNs of its frame alone, so the loop is a chain of HBM round
-        // trips (the sampled stalls of the first wave were all here, profiles/r02y_peel_M10000_ncu.csv)
-        constexpr int SU = 8;
-        for (int v0 = 0; v0 < p.n; v0 += 32 * SU) {
-            u64 cw[SU];
-#pragma unroll
-            for (int u = 0; u < SU; u++) {
-                const int v = v0 + 32 * u + lane;
-                cw[u] = v < p.n ? __ldg(chan + (size_t)v * p.W) : 0ull;
-            }
-#pragma unroll
-            for (int u = 0; u < SU; u++) {
-                const int v = v0 + 32 * u + lane;
-                if ((cw[u] >> fb) & 1ull) {
-                    n_er++;
-                    for (int i = 0; i < p.dv; i++)
-                        atomicAdd(reinterpret_cast<unsigned long long *>(st + vn_cn[(size_t)v * p.dv + i]), (1ull << 32) + (u64)v);
-                }
+        // (keeping several channel words in flight per lane here was measured slower: the registers cost resident warps)
+        for (int v0 = 0; v0 < p.n; v0 += 32) {
+            const int v = v0 + lane;
+            if (v < p.n && ((chan[(size_t)v * p.W] >> fb) & 1ull)) {
+                n_er++;
+                for (int i = 0; i < p.dv; i++)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(st + vn_cn[(size_t)v * p.dv + i]), (1ull << 32) + (u64)v);
             }
         }
 #pragma unroll
