@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) bp_window_persistent_kernel(BpParams p0, 
 __global__ void __launch_bounds__(256) bp_pos_count_kernel(BpParams p)
 {
     __shared__ int s_cnt[SCLDPC_MAX_LANES];
-    const int g = blockIdx.z, pos = blockIdx.y, ch = p.chunks;
+    const int g = graph_of(p, blockIdx.z), pos = blockIdx.y, ch = p.chunks;
     for (int i = threadIdx.x; i < p.lanes; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
     const u128 *x = p.x + ((size_t)g * p.n + (size_t)pos * p.vns_pos) * ch;
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) bp_pairs_kernel(BpParams p)
 template <int DV, int DC>
 __global__ void __launch_bounds__(256) bp_ex2_kernel(BpParams p)
 {
-    const int g = blockIdx.y, ch = p.chunks;
+    const int g = graph_of(p, blockIdx.y), ch = p.chunks;
     const int k = threadIdx.x & (ch - 1);
     const u128 mask = reinterpret_cast<const u128 *>(p.lane_mask)[g * ch + k];
     if (!nz(mask)) return;
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(256) bp_ex2_kernel(BpParams p)
 template <int DV, int DC>
 __global__ void __launch_bounds__(256) bp_pairs2_kernel(BpParams p)
 {
-    const int g = blockIdx.y, ch = p.chunks;
+    const int g = graph_of(p, blockIdx.y), ch = p.chunks;
     const u128 *x = p.x + (size_t)g * p.n * ch;
     const u128 *ex2 = p.ex2 + (size_t)g * p.nk * ch;
     const int32_t *vn_cn = p.vn_cn + (size_t)g * p.n * DV;
@@ -634,12 +634,15 @@ static void launch_count_pairs(const BpParams &p, cudaStream_t st)
     if (p.lazy_success) {
         BpParams q = p;
         q.lane_mask = p.done_mask;                              // every stopped frame is counted; the failed ones land in fail_mask
-        bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(q);
+        bp_pos_count_kernel<<<dim3(bx, p.L, graphs_in_grid(p)), 256, 0, st>>>(q);
     } else bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
     dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, 4);
     if (p.ex2 && p.lane_mask) {
         g_prof.launches += 3;
-        bp_ex2_kernel<DV, DC><<<sweep_grid((long long)p.nk << p.chunk_shift, p.G, 256, 4), 256, 0, st>>>(p);
+        gp.y = graphs_in_grid(p);                               // streams: only the graphs still decoding
+        dim3 ge = sweep_grid((long long)p.nk << p.chunk_shift, p.G, 256, 4);
+        ge.y = graphs_in_grid(p);
+        bp_ex2_kernel<DV, DC><<<ge, 256, 0, st>>>(p);
         bp_pairs2_kernel<DV, DC><<<gp, 256, 0, st>>>(p);
     } else {
         g_prof.launches += 2;

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
 {
     static_assert(DC <= 16, "neighbour index is encoded in four bit planes");
     pdl_wait_then_release();
-    const int g = blockIdx.y;
+    const int g = graph_of(p, blockIdx.y);
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS, 4) ns_iter_kernel(BpParams p)
 // (lanes are re-armed with new frames right after; a replay after that would clear bits of the new frames).
 __global__ void __launch_bounds__(32 * NS_WARPS) ns_settle_kernel(BpParams p)
 {
-    const int g = blockIdx.y;
+    const int g = graph_of(p, blockIdx.y);
     if (ld_cg(p.alive + g) == 0) return;
     const int par_prev = (p.iter & 1) ^ 1;                      // p.iter: the iteration that runs next
     const size_t plane = (size_t)g * p.n * p.chunks;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS) ns_settle_kernel(BpParams p)
 __global__ void ns_settle_done_kernel(BpParams p)
 {
     const int RW = p.nl_rw;
-    const int g = blockIdx.x, par_prev = (p.iter & 1) ^ 1;
+    const int g = graph_of(p, blockIdx.x), par_prev = (p.iter & 1) ^ 1;
     if (ld_cg(p.nl_ovf + g * 2 + par_prev) == 0) return;
     for (int i = threadIdx.x; i < RW; i += blockDim.x) p.nl_cnt[(size_t)(g * 2 + par_prev) * RW + i] = 0;
     if (threadIdx.x == 0) p.nl_ovf[g * 2 + par_prev] = 0;
@@ -278,7 +278,7 @@ __global__ void ns_settle_done_kernel(BpParams p)
 #define ARM_ROWS 128
 __global__ void __launch_bounds__(256, 4) ns_arm_kernel(BpParams p)
 {
-    const int g = blockIdx.y;
+    const int g = graph_of(p, blockIdx.y);
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_first[SCLDPC_MAX_WORDS], s_armw[SCLDPC_MAX_WORDS];
     __shared__ int s_rank[SCLDPC_MAX_WORDS + 1];
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256, 4) ns_arm_kernel(BpParams p)
 // occupied chunks only.  Frame results are stored under the frame id, so nothing downstream sees the lane change.
 __global__ void ns_compact_plan_kernel(BpParams p)
 {
-    const int g = blockIdx.x, W = p.W;
+    const int g = graph_of(p, blockIdx.x), W = p.W;
     __shared__ u64 s_act[SCLDPC_MAX_WORDS];
     __shared__ int s_rank[SCLDPC_MAX_WORDS + 1], s_go;
     __shared__ int s_fr[SCLDPC_MAX_LANES], s_it[SCLDPC_MAX_LANES];
@@ -424,7 +424,7 @@ __global__ void ns_compact_plan_kernel(BpParams p)
 #define CMP_ROWS 64
 __global__ void __launch_bounds__(256) ns_compact_kernel(BpParams p)
 {
-    const int g = blockIdx.y;
+    const int g = graph_of(p, blockIdx.y);
     const int A = ld_cg(p.cmp_cnt + g);
     if (A == 0) return;
     __shared__ unsigned short s_src[SCLDPC_MAX_LANES];
@@ -504,7 +504,7 @@ static dim3 node_grid(const BpParams &p)
     }
     long long need = (((long long)p.cn_pos_lim * p.cns_pos << p.chunk_shift) + block - 1) / block;
     long long gx = need < res ? need : res;
-    return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+    return dim3((unsigned)(gx < 1 ? 1 : gx), graphs_in_grid(p), 1);
 }
 
 template <int DV, int DC>
@@ -552,7 +552,7 @@ void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st)
 {
     g_prof.launches += 2;
     ns_settle_kernel<<<node_grid_any(dv, dc, p), 32 * NS_WARPS, 0, st>>>(p);
-    ns_settle_done_kernel<<<p.G, 256, 0, st>>>(p);
+    ns_settle_done_kernel<<<graphs_in_grid(p), 256, 0, st>>>(p);
 }
 
 void bp_launch_node_arm(const BpParams &p, cudaStream_t st)
@@ -562,15 +562,31 @@ void bp_launch_node_arm(const BpParams &p, cudaStream_t st)
     long long need = ((long long)p.n + ARM_ROWS - 1) / ARM_ROWS;
     long long gx = need < res ? need : res;
     g_prof.launches += 1;
-    ns_arm_kernel<<<dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G), 256, 0, st>>>(p);
+    ns_arm_kernel<<<dim3((unsigned)(gx < 1 ? 1 : gx), graphs_in_grid(p)), 256, 0, st>>>(p);
 }
 
 // after the harvest and the arming: graphs in the tail of their stream move their live frames into the lowest lanes
 void bp_launch_node_compact(const BpParams &p, cudaStream_t st)
 {
     g_prof.launches += 2;
-    ns_compact_plan_kernel<<<p.G, 256, 0, st>>>(p);
-    ns_compact_kernel<<<dim3(592, (unsigned)p.G), 256, 0, st>>>(p);
+    ns_compact_plan_kernel<<<graphs_in_grid(p), 256, 0, st>>>(p);
+    ns_compact_kernel<<<dim3(592, graphs_in_grid(p)), 256, 0, st>>>(p);
+}
+
+// list of the graphs still decoding after this harvest (ascending), for the grids of the launches the host enqueues once it has
+// seen this harvest's counters
+__global__ void ns_alive_list_kernel(BpParams p, int parity)
+{
+    if (threadIdx.x != 0) return;
+    int *list = p.glist2 + (size_t)parity * p.G, n = 0;
+    for (int g = 0; g < p.G; g++)
+        if (p.alive[g]) list[n++] = g;
+    p.alive_total[6 + parity] = n;
+}
+void bp_launch_node_alive_list(const BpParams &p, int parity, cudaStream_t st)
+{
+    g_prof.launches += 1;
+    ns_alive_list_kernel<<<1, 32, 0, st>>>(p, parity);
 }
 
 void bp_launch_node_tables(const BpParams &p, cudaStream_t st)

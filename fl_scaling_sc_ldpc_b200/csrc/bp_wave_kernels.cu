@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams
 // harvest step 3 (one block per graph): results of the lanes in done_mask, then re-arm them with the next frame ids
 __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
 {
-    const int g = blockIdx.x, L = p.L, W = p.W, B = p.frames_per_graph;
+    const int g = graph_of(p, blockIdx.x), L = p.L, W = p.W, B = p.frames_per_graph;
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ int s_rank[SCLDPC_MAX_WORDS + 1];
     __shared__ u64 s_done[SCLDPC_MAX_WORDS], s_arm[SCLDPC_MAX_WORDS];
@@ -738,7 +738,7 @@ void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st)
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st)
 {
     g_prof.launches += 1;
-    bp_stream_harvest_kernel<<<p.G, 256, 0, st>>>(p, exp_all);
+    bp_stream_harvest_kernel<<<graphs_in_grid(p), 256, 0, st>>>(p, exp_all);
 }
 
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st)

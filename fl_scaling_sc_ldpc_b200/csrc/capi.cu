@@ -26,6 +26,7 @@ int bp_launch_node_iteration(int dv, int dc, const BpParams &p, bool after_harve
 void bp_launch_node_settle(int dv, int dc, const BpParams &p, cudaStream_t st);
 void bp_launch_node_arm(const BpParams &p, cudaStream_t st);
 void bp_launch_node_compact(const BpParams &p, cudaStream_t st);
+void bp_launch_node_alive_list(const BpParams &p, int parity, cudaStream_t st);
 void bp_launch_node_tables(const BpParams &p, cudaStream_t st);
 int bp_launch_window_node_iteration(int dv, int dc, const BpParams &p, cudaStream_t st, int blocks_per_sm);
 void bp_launch_window_node_init(const BpParams &p, cudaStream_t st, bool resume);
@@ -228,6 +229,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
             q.nl_list = c.take<uint2>(G * 2 * RW * (size_t)q.nl_stride);
             q.nl_cnt = c.take<int>(G * 2 * RW);
             q.nl_ovf = c.take<int>(G * 2);
+            q.glist2 = c.take<int>(2 * G);
             q.gshift = c.take<int>(G);
             q.cmp_cnt = c.take<int>(G);
             q.cmp_src = c.take<int>(G * lanes);
@@ -699,7 +701,8 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
     // (profiles/r02h_harvest_period_ab.txt: 5.62 .. 5.82e13 edge-updates/s for constants 25 .. 60 and both policies).
     const int hc10 = env_int("SCLDPC_HARVEST_C10", 60, 1, 1000);
     const int h_policy_max = env_int("SCLDPC_HARVEST_POLICY", 0, 0, 1);
-    const bool compact = env_int("SCLDPC_COMPACT", 1, 0, 1) != 0;   // lane compaction in the tail of a stream (A/B switch)
+    const bool compact = env_int("SCLDPC_COMPACT", 1, 0, 1) != 0;
+    const bool glists = env_int("SCLDPC_ALIVE_GRIDS", 1, 0, 1) != 0;   // grids sized by the graphs still decoding (A/B switch)   // lane compaction in the tail of a stream (A/B switch)
     int H = adaptive ? 16 : cfg->harvest_every;
     CU(cudaMemsetAsync(p.alive_total + 1, 0, 2 * sizeof(int), st));
     CU(cudaMemsetAsync(p.alive_total + 4, 0x7f, 2 * sizeof(int), st));
@@ -725,6 +728,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
         if (node) bp_launch_node_arm(p, st);
         if (node && compact) bp_launch_node_compact(p, st);
+        if (node && glists) bp_launch_node_alive_list(p, slot, st);
         CU_LAUNCHES();
         CU(cudaMemcpyAsync(hf + 8 * slot, p.alive_total, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
@@ -735,6 +739,11 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
             CU(cudaEventSynchronize(ev[prev]));
             pending[prev] = false;
             if (hf[8 * prev] == 0) break;
+            if (node && glists) {                                // grids of the next chunk: the graphs that were alive at that harvest
+                p.glist = p.glist2 + (size_t)prev * p.G;
+                p.n_glist = hf[8 * prev + 6 + prev];
+                if (p.n_glist < 1 || p.n_glist > p.G) { p.glist = nullptr; p.n_glist = 0; }
+            }
             int mean_it = hf[8 * prev + 1 + prev];
             if (!h_policy_max && hf[8 * prev + 4 + prev] != 0x7f7f7f7f) mean_it = hf[8 * prev + 4 + prev];
             if (adaptive && mean_it > 0) {

@@ -261,6 +261,10 @@ struct BpParams {
     int nl_cap;               // entries of a region in use (nl_stride; SCLDPC_LIST_CAP lowers it so that tests reach the overflow path)
     int nl_rw;                // regions per graph and parity: 8 warps x blocks of the largest sweep, at most NS_MAX_BLOCKS*NS_WARPS
     int *nl_ovf;              // [G][2] some region overflowed: the other plane catches up by a full pass instead
+    const int *glist;         // node-state streams: graphs that were still decoding at the last harvest the host has seen (ascending;
+    int n_glist;              //   NULL: all G).  Grids are sized by this list, so finished graphs cost no blocks at all (4 graphs per batch,
+                              //   one still decoding: 1776 of 2368 blocks of every iteration launch did nothing but exit, 6 us of 58)
+    int *glist2;              // [2][G] the lists written by the last two harvests (by harvest parity); count in alive_total[6 + parity]
     int *gshift;              // [G] node-state streams: log2 of the 128-lane chunks the graph's live frames occupy (chunk_shift until the
                               //   tail of the stream, then lowered by the lane compaction, bp_node_kernels.cu)
     int *cmp_cnt;             // [G] lanes moved by the compaction planned at this harvest (0: none)
@@ -297,6 +301,10 @@ struct BpParams {
     int row;                  // trajectory row written by this iteration (-1: none)
     long long win_edges;      // edge updates of one iteration of the current sweep ranges
 };
+
+// graph handled by block coordinate b of a grid that is sized by the list of graphs still decoding
+__device__ __forceinline__ int graph_of(const BpParams &p, unsigned b) { return p.glist ? p.glist[b] : (int)b; }
+static inline unsigned graphs_in_grid(const BpParams &p) { return (unsigned)(p.glist ? p.n_glist : p.G); }
 
 // ---- per-warp resolution lists of the node-state sweeps (bp_node_kernels.cu, bp_window_node_kernels.cu) ----------------
 // replay of one warp's region of the previous launch on plane `w` (32-bit words of graph g)
