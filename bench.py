@@ -627,7 +627,7 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: K steps ------------------------------------------------------------------------------------
-    prof = SweepProfile(lib, _lib.check, every=13)       # co-prime with the harvest periods in use
+    prof = SweepProfile(lib, _lib.check, every=29)       # co-prime with the harvest periods in use; a sampled launch is not a programmatic dependent
     lib.scldpc_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -460,8 +460,12 @@ __global__ void __launch_bounds__(256) bp_pairs2_kernel(BpParams p)
         if (!nz(cand)) continue;
         int cs[DV];
         load_row<DV>(vn_cn + (size_t)a * DV, cs);
+        // the first CN alone rejects most rows (in a stalled frame about a fifth of the CNs have exactly two erased neighbours), so
+        // the other dv-1 gathers wait for it: less than half the rows of the plane the one-shot AND fetched
+        cand &= ld_stream(ex2 + (size_t)cs[0] * ch + k);
+        if (!nz(cand)) continue;
 #pragma unroll
-        for (int i = 0; i < DV; i++) cand &= ld_stream(ex2 + (size_t)cs[i] * ch + k);
+        for (int i = 1; i < DV; i++) cand &= ld_stream(ex2 + (size_t)cs[i] * ch + k);
         for (int half = 0; half < 2; half++) {
             u64 m = half ? cand.y : cand.x;
             while (m) {

@@ -499,15 +499,14 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
     __shared__ u64 s_done[SCLDPC_MAX_WORDS], s_arm[SCLDPC_MAX_WORDS];
     __shared__ int s_frames;
     __shared__ unsigned long long s_its;
+    // (the word loops of this kernel run one word per thread: as thread-0 loops they were chains of dependent global round trips,
+    // two thirds of the kernel's 21 us)
+    if (threadIdx.x < W) { s_done[threadIdx.x] = p.done_mask[g * W + threadIdx.x]; s_arm[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { s_frames = 0; s_its = 0; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        s_frames = 0; s_its = 0;
         int r = 0;
-        for (int w = 0; w < W; w++) {
-            s_done[w] = p.done_mask[g * W + w];
-            s_arm[w] = 0;
-            s_rank[w] = r;
-            r += __popcll(s_done[w]);
-        }
+        for (int w = 0; w < W; w++) { s_rank[w] = r; r += __popcll(s_done[w]); }
         s_rank[W] = r;
     }
     __syncthreads();
@@ -580,18 +579,24 @@ __global__ void bp_stream_harvest_kernel(BpParams p, int exp_all)
         } else p.lane_frame[g * p.lanes + l] = -1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 any = 0;
-        for (int w = 0; w < W; w++) {
-            p.done_mask[g * W + w] = 0;
-            p.fail_mask[g * W + w] = 0;
-            p.arm_mask[g * W + w] = s_arm[w];
-            any |= s_arm[w] | p.active[g * W + w];
-            if (p.lazy_success) {                               // ns_arm_kernel writes the new frames before the next iteration
-                p.active[g * W + w] |= s_arm[w];
-                p.noprog[g * W + w] = 0;
-            }
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (threadIdx.x < W) {
+        const int w = threadIdx.x;
+        const u64 act = p.active[g * W + w];
+        p.done_mask[g * W + w] = 0;
+        p.fail_mask[g * W + w] = 0;
+        p.arm_mask[g * W + w] = s_arm[w];
+        if (s_arm[w] | act) s_any = 1;
+        if (p.lazy_success) {                                   // ns_arm_kernel writes the new frames before the next iteration
+            p.active[g * W + w] = act | s_arm[w];
+            p.noprog[g * W + w] = 0;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int any = s_any;
         const int nn = next0 + s_rank[W];
         p.next_frame[g] = nn < B ? nn : B;
         if (!any) { p.alive[g] = 0; atomicSub(p.alive_total, 1); }
