@@ -633,14 +633,16 @@ int bp_launch_iteration(int dv, int dc, const BpParams &p, bool traj, bool freez
 template <int DV, int DC>
 static void launch_count_pairs(const BpParams &p, cudaStream_t st)
 {
+    // blocks per position: 8 left two thirds of the SMs idle in the streams' harvests (400 blocks of 39 dependent trips each,
+    // profiles/r02ze_harvest_kernels_ncu.csv); the pair search takes 8 blocks per SM for the same reason (32 registers)
     int bx = (p.vns_pos * p.chunks + 255) / 256;
-    if (bx > 8) bx = 8;
+    if (bx > (p.lazy_success ? 32 : 8)) bx = p.lazy_success ? 32 : 8;
     if (p.lazy_success) {
         BpParams q = p;
         q.lane_mask = p.done_mask;                              // every stopped frame is counted; the failed ones land in fail_mask
         bp_pos_count_kernel<<<dim3(bx, p.L, graphs_in_grid(p)), 256, 0, st>>>(q);
     } else bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
-    dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, 4);
+    dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, (p.ex2 && p.lane_mask) ? 8 : 4);
     if (p.ex2 && p.lane_mask) {
         g_prof.launches += 3;
         gp.y = graphs_in_grid(p);                               // streams: only the graphs still decoding

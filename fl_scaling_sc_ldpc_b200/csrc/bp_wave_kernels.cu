@@ -743,7 +743,7 @@ void bp_launch_stream_init(const BpParams &p, int n_lanes_used, cudaStream_t st)
 void bp_launch_stream_harvest(const BpParams &p, int exp_all, cudaStream_t st)
 {
     g_prof.launches += 1;
-    bp_stream_harvest_kernel<<<graphs_in_grid(p), 256, 0, st>>>(p, exp_all);
+    bp_stream_harvest_kernel<<<graphs_in_grid(p), 1024, 0, st>>>(p, exp_all);   // one warp per failed frame: 32 at a time
 }
 
 void bp_launch_wave_init(const BpParams &p, cudaStream_t st)
