@@ -577,11 +577,15 @@ void bp_launch_node_compact(const BpParams &p, cudaStream_t st)
 // seen this harvest's counters
 __global__ void ns_alive_list_kernel(BpParams p, int parity)
 {
-    if (threadIdx.x != 0) return;
-    int *list = p.glist2 + (size_t)parity * p.G, n = 0;
-    for (int g = 0; g < p.G; g++)
-        if (p.alive[g]) list[n++] = g;
-    p.alive_total[6 + parity] = n;
+    int *list = p.glist2 + (size_t)parity * p.G, n = 0;                 // one warp: ballot + prefix, 32 graphs per trip
+    const int lane = threadIdx.x & 31;
+    for (int g0 = 0; g0 < p.G; g0 += 32) {
+        const bool a = g0 + lane < p.G && p.alive[g0 + lane] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (a) list[n + __popc(m & ((1u << lane) - 1u))] = g0 + lane;
+        n += __popc(m);
+    }
+    if (lane == 0) p.alive_total[6 + parity] = n;
 }
 void bp_launch_node_alive_list(const BpParams &p, int parity, cudaStream_t st)
 {

@@ -212,3 +212,19 @@ def test_lane_compaction_in_the_tail_changes_nothing(lanes, B, cap, monkeypatch,
             assert (getattr(a, key) == ref[key]).all() and (getattr(b, key) == ref[key]).all(), (H, key)
         if H == 1 and cap == 0:                                  # every iteration is a chance to compact
             assert n_cmp >= 3 and moved >= n_cmp, (n_cmp, moved)
+
+
+def test_many_graphs_finishing_at_different_times(monkeypatch):
+    """40 graphs with channels from easy to hopeless: graphs finish at very different times, the grids of the stream kernels
+    shrink to the list of graphs still decoding (more than one ballot word of graphs); with and without that list"""
+    G = 40
+    ens = eng.Ensemble(4, 8, 10, 32)
+    fbg = eng.FrameBatch(ens, G, 64).generate_graphs(51, first_graph_id=3)
+    eps = [0.30 + 0.24 * (g % 7) / 6 for g in range(G)]
+    ref = sync_reference(fbg, ens, 150, eps, 13, True)
+    for grids in ("1", "0"):
+        monkeypatch.setenv("SCLDPC_ALIVE_GRIDS", grids)
+        for H in (1, 0):
+            s = eng.decode_bp_stream(fbg, 150, eps, 13, first_graph_id=3, harvest_every=H)
+            for key in KEYS:
+                assert (getattr(s, key) == ref[key]).all(), (grids, H, key)
