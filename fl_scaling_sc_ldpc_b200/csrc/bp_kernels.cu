@@ -641,7 +641,7 @@ static void launch_count_pairs(const BpParams &p, cudaStream_t st)
         BpParams q = p;
         q.lane_mask = p.done_mask;                              // every stopped frame is counted; the failed ones land in fail_mask
         bp_pos_count_kernel<<<dim3(bx, p.L, graphs_in_grid(p)), 256, 0, st>>>(q);
-    } else bp_pos_count_kernel<<<dim3(bx, p.L, p.G), 256, 0, st>>>(p);
+    } else bp_pos_count_kernel<<<dim3(bx, p.L, graphs_in_grid(p)), 256, 0, st>>>(p);
     dim3 gp = sweep_grid((long long)p.n << p.chunk_shift, p.G, 256, (p.ex2 && p.lane_mask) ? 8 : 4);
     if (p.ex2 && p.lane_mask) {
         g_prof.launches += 3;

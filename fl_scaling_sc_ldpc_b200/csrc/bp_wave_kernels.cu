@@ -48,7 +48,7 @@ __global__ void bp_wave_init_kernel(BpParams p)
 template <int DC, bool TRAJ, bool HEAD = false>
 __global__ void __launch_bounds__(256, (TRAJ || HEAD) ? 3 : 5) bp_cn_wave_kernel(BpParams p)
 {
-    const int g = blockIdx.y;
+    const int g = graph_of(p, blockIdx.y);
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ int s_cnt[TRAJ ? SCLDPC_MAX_LANES : 1];
     __shared__ u128 s_planes[TRAJ ? LC_PLANES * 256 : 1];
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256, ARM ? 3 : 4) bp_vn_stream_kernel(BpParams
 {
     // The CN sweep walks graphs and positions upwards; this sweep walks them downwards (vn_reverse), so each sweep starts on
     // the rows the other one touched last -- its first gathers (and the x / y rows) are L2 hits instead of HBM reads.
-    const int g = p.vn_reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int g = graph_of(p, p.vn_reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y);
     if (ld_cg(p.alive + g) == 0) return;
     __shared__ u64 s_new[SCLDPC_MAX_WORDS], s_er[SCLDPC_MAX_WORDS];
     __shared__ int s_last;
@@ -704,7 +704,7 @@ static void launch_stream_iteration(const BpParams &p, bool arm, cudaStream_t st
     auto grid = [&](int resident, long long items_per_graph) {
         long long need = (items_per_graph + block - 1) / block;
         long long gx = need < resident ? need : resident;
-        return dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)p.G, 1);
+        return dim3((unsigned)(gx < 1 ? 1 : gx), graphs_in_grid(p), 1);
     };
     dim3 gc = grid(res_cn, (long long)p.cn_pos_lim * p.cns_pos << p.chunk_shift);
     dim3 gv = grid(res_vn, (long long)p.n << p.chunk_shift);

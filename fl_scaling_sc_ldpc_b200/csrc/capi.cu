@@ -219,6 +219,7 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
         q.xb = c.take<u128>(G * n * ch + ch);                         //   behind the last graph stands in for absent CN edges
         q.ex2 = c.take<u128>(G * nk * ch);
         q.first_new = c.take<u64>(G * W);
+        q.glist2 = c.take<int>(2 * G);
         if (no_msgs) {
             const size_t RW = list_regions(nk, ch);
             q.nl_rw = (int)RW;
@@ -229,7 +230,6 @@ static size_t carve(const scldpc_dims_t *d, uint32_t flags, void *ws, BpParams *
             q.nl_list = c.take<uint2>(G * 2 * RW * (size_t)q.nl_stride);
             q.nl_cnt = c.take<int>(G * 2 * RW);
             q.nl_ovf = c.take<int>(G * 2);
-            q.glist2 = c.take<int>(2 * G);
             q.gshift = c.take<int>(G);
             q.cmp_cnt = c.take<int>(G);
             q.cmp_src = c.take<int>(G * lanes);
@@ -728,7 +728,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
         bp_launch_stream_harvest(p, (cfg->flags & SCLDPC_F_EXP_ALL) ? 1 : 0, st);
         if (node) bp_launch_node_arm(p, st);
         if (node && compact) bp_launch_node_compact(p, st);
-        if (node && glists) bp_launch_node_alive_list(p, slot, st);
+        if (glists) bp_launch_node_alive_list(p, slot, st);
         CU_LAUNCHES();
         CU(cudaMemcpyAsync(hf + 8 * slot, p.alive_total, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(ev[slot], st));
@@ -739,7 +739,7 @@ extern "C" int scldpc_bp_stream(const scldpc_dims_t *d, const scldpc_batch_t *b,
             CU(cudaEventSynchronize(ev[prev]));
             pending[prev] = false;
             if (hf[8 * prev] == 0) break;
-            if (node && glists) {                                // grids of the next chunk: the graphs that were alive at that harvest
+            if (glists) {                                        // grids of the next chunk: the graphs that were alive at that harvest
                 p.glist = p.glist2 + (size_t)prev * p.G;
                 p.n_glist = hf[8 * prev + 6 + prev];
                 if (p.n_glist < 1 || p.n_glist > p.G) { p.glist = nullptr; p.n_glist = 0; }
