@@ -14,12 +14,15 @@ per graph).  Graph ids are global and never repeat: every step, warm-up included
 Throughput counts USEFUL work only: edge-updates = sum over frames of (iterations that frame executed) * 2E, the same
 formula as for the CPU; iterations a finished frame rides along for do not count.
 
-value    : the step above, everything on the device.
+value    : the step above, everything on the device; --pipeline batches (default 2) are in flight at a time, each on its own
+           host thread and CUDA stream, so the tail of one batch's frame streams runs behind the next batch (`sequential` in the
+           line: the same steps one batch after the other).
 e2e      : the same step through the host-buffer C-ABI call scldpc_stream_host: graph tables start in pinned HOST memory
            (a different set every step), per-frame results end in host memory; H2D / D2H inside the timed region.
 roofline : one flooding iteration of the stream decoder (ns_iter_kernel, bp_node_kernels.cu): algorithmic bytes
            B_alg = (4E+n)/8 per useful frame-iteration (the message formulation's figure) over the CUDA-event
-           time of sampled launches inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth; ncu's DRAM
+           time of sampled launches (in the sequential segment, where a launch's elapsed time is its own), against
+           MEASURED_PEAKS.json's HBM copy bandwidth; ncu's DRAM
            bytes and the node-state minimum are reported beside it.
 workloads: (N = 1 only) the other BASELINE configs, each timed on the device with its own roofline and CPU baseline:
            turnover at 1024 frames per graph, message-passing sweeps, peeling trajectories (config 1), capped BP with
@@ -73,6 +76,7 @@ def make_config(args) -> dict:
             "graph_turnover": "new graphs every step, generated and indexed on the device inside the timed region; no "
                               "(graph, frame) realisation is decoded twice",
             "l2": f"inputs larger than L2 (126 MB): about {state_mb} MB of decoder state per batch, rewritten every step",
+            "batches_in_flight": (max(1, getattr(args, "pipeline", 1)) if stream_mode else 1),
             "seed": args.seed}
 
 
@@ -593,58 +597,127 @@ def run_ours(args):
     def gid_of(step_index):
         return (step_index * world + rank) * G
 
-    fb = eng.FrameBatch(ens, G, lanes, N_WORDS, device=dev)
-    counters = torch.zeros(4, dtype=torch.int64, device=dev)   # frame-iterations, frames, frame errors, bit errors
+    # Batches in flight: P host threads, each with its own CUDA stream, device buffers and scldpc_bp_stream calls, take the steps
+    # in turn -- the tail of one batch's frame streams (no frames left to hand out: ~1500 short launches) runs behind the next
+    # batch instead of in front of it.  Same work and same realisations as one batch after the other (`sequential` in the line).
+    import threading
+    P = max(1, args.pipeline) if stream_mode else 1
+    fbs = [eng.FrameBatch(ens, G, lanes, N_WORDS, device=dev) for _ in range(P)]
+    fb = fbs[0]
+    cuda_streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+    counters_t = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(P)]   # frame-iterations, frames, frame errors, bit errors
     iters_launched = [0]                                       # iterations launched by this rank in the timed region
     graph_events = []
+    lock = threading.Lock()
 
-    def step(s, acc=True):
+    def step(s, acc=True, t=0):
+        fbt = fbs[t]
         gid = gid_of(s)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        fb.generate_graphs(seed=args.seed, first_graph_id=gid)         # scldpc_graph_generate + scldpc_graph_build_tables
+        fbt.generate_graphs(seed=args.seed, first_graph_id=gid)        # scldpc_graph_generate + scldpc_graph_build_tables
         g1.record()
         if stream_mode:
-            res, launched = eng.decode_bp_stream(fb, B, eps, args.seed + 1, first_graph_id=gid, harvest_every=args.harvest_every, collect=False)
+            res, launched = eng.decode_bp_stream(fbt, B, eps, args.seed + 1, first_graph_id=gid, harvest_every=args.harvest_every, collect=False)
             it, resid = res[0].to(torch.int64), res[1].to(torch.int64)
         else:
-            fb.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid)
-            res, erased, rows, launched = eng.decode_bp_full(fb, eng.UNLIMITED, True, collect=False)
+            fbt.generate_erasures(eps, seed=args.seed + 1, first_graph_id=gid)
+            res, erased, rows, launched = eng.decode_bp_full(fbt, eng.UNLIMITED, True, collect=False)
             it, resid = res[0, :, :lanes].to(torch.int64), res[1, :, :lanes].to(torch.int64)
         if acc:
-            graph_events.append((g0, g1))
-            iters_launched[0] += int(launched)
-            counters.add_(torch.stack([it.sum(), torch.tensor(it.numel(), device=dev), (resid > 0).sum(), resid.sum()]))
+            with lock:
+                graph_events.append((g0, g1))
+                iters_launched[0] += int(launched)
+            counters_t[t].add_(torch.stack([it.sum(), torch.tensor(it.numel(), device=dev), (resid > 0).sum(), resid.sum()]))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(first, count, acc, pipes, sample_every=0):
+        """steps first .. first+count-1 with `pipes` batches in flight; returns (device ms, launches, sampled sweep times)"""
+        out = {"launches": 0, "prof": (np.zeros(0), np.zeros(0)), "err": None}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def worker(t):
+            try:
+                torch.cuda.set_device(local_rank)
+                with torch.cuda.stream(cuda_streams[t]):
+                    lib.scldpc_launch_count(1)                 # the launch counter and the sampler are per host thread
+                    prof = SweepProfile(lib, _lib.check, every=sample_every) if (sample_every and t == 0) else None
+                    for i in range(t, count, pipes):
+                        step(first + i, acc, t)
+                    cuda_streams[t].synchronize()
+                    n = int(lib.scldpc_launch_count(1))
+                    pr = prof.end() if prof is not None else None
+                with lock:
+                    out["launches"] += n
+                    if pr is not None:
+                        out["prof"] = pr
+            except Exception as e:  # pragma: no cover
+                out["err"] = e
+
+        barrier()
+        ev0.record()
+        if pipes == 1:
+            lib.scldpc_launch_count(1)
+            prof = SweepProfile(lib, _lib.check, every=sample_every) if sample_every else None
+            for i in range(count):
+                step(first + i, acc, 0)
+            ev1.record()
+            torch.cuda.synchronize()
+            out["launches"] = int(lib.scldpc_launch_count(1))
+            if prof is not None:
+                out["prof"] = prof.end()
+        else:
+            th = [threading.Thread(target=worker, args=(t,)) for t in range(pipes)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            if out["err"] is not None:
+                raise out["err"]
+            torch.cuda.synchronize()
+            ev1.record()
+            torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1), out["launches"], out["prof"]
+
     clocks = ClockSampler(local_rank)
-    for i in range(args.warmup):
-        step(i, acc=False)
+    run_steps(0, args.warmup, False, P)
     barrier()
 
     # ---- timed region: K steps ------------------------------------------------------------------------------------
-    prof = SweepProfile(lib, _lib.check, every=29)       # co-prime with the harvest periods in use; a sampled launch is not a programmatic dependent
-    lib.scldpc_launch_count(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     clocks.mark(True)
-    ev0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record()
+    # sampling every 29th iteration: co-prime with the harvest periods in use; a sampled launch is not a programmatic dependent
+    ms_local, launches, (cn_ms, vn_ms) = run_steps(args.warmup, args.steps, True, P, sample_every=29 if P == 1 else 0)
     barrier()
     clocks.mark(False)
-    ms_local = ev0.elapsed_time(ev1)
-    launches = lib.scldpc_launch_count(1)
     clk = clocks.stop()
-    cn_ms, vn_ms = prof.end()
     graph_ms = sum(a.elapsed_time(b) for a, b in graph_events)
+    counters = torch.stack(counters_t).sum(0)
 
     local_frame_iters = int(counters[0].item())
+    # The same steps one batch after the other (a few of them): the comparison figure for the batches in flight, and the segment
+    # in which the iteration launches are sampled for the roofline -- with two batches in flight the kernels of the two streams
+    # interleave, and the elapsed time of a launch is not its own.
+    sequential = None
+    roof_fi, roof_il = local_frame_iters, iters_launched[0]
+    if P > 1:
+        n_seq = min(args.steps, 4)
+        il0 = iters_launched[0]
+        seq_ms, _, (cn_ms, vn_ms) = run_steps(args.warmup + 2 * args.steps + 4, n_seq, True, 1, sample_every=29)
+        seq_fi = int(torch.stack(counters_t).sum(0)[0].item()) - local_frame_iters
+        roof_fi, roof_il = seq_fi, iters_launched[0] - il0
+        sq = torch.tensor([seq_ms, float(seq_fi)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = sq[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = sq[1:].clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            sq = torch.cat([mx, sm])
+        sequential = {"value": float(sq[1].item()) * 2.0 * E_EDGES / (float(sq[0].item()) * 1e-3), "unit": "edge-updates/s", "steps": n_seq,
+                      "what": "the same step, one batch after the other on one stream (no batches in flight); the roofline's launch "
+                              "durations are sampled here"}
     tmax = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     tot = counters.clone()
     if world > 1:
@@ -661,7 +734,7 @@ def run_ours(args):
         tj = _traffic()
         n_s = len(cn_ms)
         cn_avg, vn_avg = float(cn_ms.mean()) * 1e-3, float(vn_ms.mean()) * 1e-3
-        fi_per_launch = local_frame_iters / max(1, iters_launched[0])
+        fi_per_launch = roof_fi / max(1, roof_il)
         pct = lambda a, q: float(np.percentile(a, q))
         if not messages:
             # Node-state sweeps.  SURVEY 8(d): the denominator of record stays the message formulation's B_alg = (4E+n)/8 B per
@@ -678,6 +751,7 @@ def run_ours(args):
             traffic = tn.get("iteration_dram_bytes_per_launch")
             roof = {"bound": "hbm", "kernel": kname, "kernel_does": kwhat, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_note": tn.get("note"), "peak_source": peak_src, "launches_sampled": n_s,
+                    "sampled_in": "the timed region" if P == 1 else "the sequential segment that follows the timed region (see `sequential`)",
                     "avg_launch_ms": 1e3 * it_t, "p10_p50_p90_ms": [pct(cn_ms + vn_ms, 10), pct(cn_ms + vn_ms, 50), pct(cn_ms + vn_ms, 90)],
                     "frame_iterations_per_launch": fi_per_launch,
                     "algorithmic_bytes": "(4E+n)/8 B = 1.0625 MB per useful frame-iteration (message formulation, SURVEY 8d: the denominator of record)",
@@ -712,17 +786,18 @@ def run_ours(args):
         fb.generate_graphs(seed=args.seed, first_graph_id=gid_of(e2e_base + j))
         h_vn.append(fb.vn_cn.cpu().pin_memory())
     if stream_mode:
-        outs = [torch.zeros((G, B), dtype=torch.int32).pin_memory() for _ in range(5)]
+        outs_t = [[torch.zeros((G, B), dtype=torch.int32).pin_memory() for _ in range(5)] for _ in range(P)]
+        outs = outs_t[0]
         cfgs = [_lib.StreamCfg(B, args.harvest_every, _lib.F_TERMINATED | sflag, 0, 0, eps_arr.ctypes.data_as(ctypes.c_void_p).value, None, None, None,
                                args.seed + 1, gid_of(e2e_base + j), 0) for j in range(n_e2e)]
         h2d = int(h_vn[0].numel() * 4)
         d2h = int(5 * G * B * 4)
         api = "scldpc_stream_host (graph tables in pinned host memory, a new set every step; channel realisations drawn on the device)"
 
-        def e2e_step(j):
+        def e2e_step(j, t=0):
             _lib.check(lib.scldpc_stream_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[j].data_ptr()), ctypes.byref(cfgs[j]),
-                                              *[ctypes.c_void_p(o.data_ptr()) for o in outs], None))
-            return int(outs[0].sum().item())
+                                              *[ctypes.c_void_p(o.data_ptr()) for o in outs_t[t]], None))
+            return int(outs_t[t][0].sum().item())
     else:
         h_ch = []
         for j in range(n_e2e):
@@ -734,7 +809,7 @@ def run_ours(args):
         d2h = int(6 * G * lanes * 4)
         api = "scldpc_decode_host (graph tables + bit-sliced channel words in pinned host memory)"
 
-        def e2e_step(j):
+        def e2e_step(j, t=0):
             _lib.check(lib.scldpc_decode_host(ctypes.byref(dims), ctypes.c_void_p(h_vn[j].data_ptr()),
                                               ctypes.c_void_p(h_ch[j].data_ptr()), 0, 0, 0, flags,
                                               *[ctypes.c_void_p(o.data_ptr()) for o in outs], None, None, None, 0))
@@ -744,9 +819,21 @@ def run_ours(args):
         e2e_step(j)
     barrier()
     t0 = time.perf_counter()
-    e_iters = 0
-    for j in range(args.steps):
-        e_iters += e2e_step(nw_e2e + j)          # the call returns after its D2H copy has completed
+    e_parts = [0] * P
+
+    def e2e_worker(t):
+        for j in range(t, args.steps, P):
+            e_parts[t] += e2e_step(nw_e2e + j, t)    # the call returns after its D2H copy has completed
+
+    if P == 1:
+        e2e_worker(0)
+    else:                                            # P host threads, each call on its own thread's stream inside the library
+        th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(P)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+    e_iters = sum(e_parts)
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
     et = torch.tensor([e_dt], dtype=torch.float64, device=dev)
@@ -758,7 +845,7 @@ def run_ours(args):
            "frames_per_s": world * args.steps * G * B / float(et.item()),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api}
     need = lib.scldpc_bp_stream_workspace_bytes(ctypes.byref(dims), sflag) if stream_mode else fb.workspace(_lib.F_TERMINATED | sflag).numel()
-    del fb, h_vn
+    del fb, fbs, h_vn
     torch.cuda.empty_cache()
 
     workloads = None
@@ -780,7 +867,7 @@ def run_ours(args):
             "frame_error_rate": ferr / max(1, frames), "bit_error_rate": berr / max(1, frames) / N_VNS,
             "graph_generation": {"ms_per_generated_graph": graph_ms / max(1, args.steps * G), "share_of_step": graph_ms / max(1e-9, ms_local),
                                  "what": "scldpc_graph_generate (Philox keys + bitonic sort per CN position) + scldpc_graph_build_tables, rank 0"},
-            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roof, "kernels": kernels,
+            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "sequential": sequential, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu_baseline, "workloads": workloads,
         }
         print(json.dumps(line))
@@ -807,6 +894,7 @@ def main():
     ap.add_argument("--mode", default="stream", choices=["stream", "batch"],
                     help="stream: lane recycling over --frames-per-graph frames per graph; batch: one frame per lane")
     ap.add_argument("--frames-per-graph", type=int, default=FRAMES_PER_STREAM)
+    ap.add_argument("--pipeline", type=int, default=2, help="stream mode: batches in flight (host threads x CUDA streams); 1 = one batch after the other")
     ap.add_argument("--harvest-every", type=int, default=0, help="stream mode: iterations between harvests (0: adaptive)")
     args = ap.parse_args()
     N_WORDS = args.n_words

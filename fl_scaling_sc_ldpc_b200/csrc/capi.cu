@@ -59,7 +59,7 @@ void peel_variance_launch(const int32_t *r1, int n_frames, int row_len, const do
 
 using namespace scldpc;
 
-namespace scldpc { Profiler g_prof = {0, 0, 0, 0, nullptr, nullptr}; }
+namespace scldpc { thread_local Profiler g_prof = {0, 0, 0, 0, nullptr, nullptr}; }
 
 static thread_local char g_err[512] = "";
 
@@ -1102,9 +1102,19 @@ extern "C" int scldpc_profile_end(int *n_samples, int *iter_idx, float *cn_ms, f
 // once), so repeated calls do not pay cudaMalloc / cudaFree.
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
-    int alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, nullptr) == cudaSuccess ? 0 : -1; }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes, cudaStream_t s = nullptr) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s) == cudaSuccess ? 0 : -1; }
 };
+
+// The host-buffer entry points work on a stream of the calling host thread, so that calls from different host threads overlap
+// on the device (two batches in flight hide the tail of one batch's frame streams behind the next batch, bench.py).
+static cudaStream_t host_call_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+    return s;
+}
 
 static void keep_pool_memory()
 {
@@ -1134,10 +1144,10 @@ extern "C" int scldpc_stream_host(const scldpc_dims_t *d, const int32_t *vn_cn_h
     const size_t n = (size_t)d->L * d->vns_pos, nk = (size_t)(d->L + d->dv - 1) * d->cns_pos, E = n * d->dv;
     DevBuf vn_cn, vn_slot, cn_edge, scratch, ws, res;
     const size_t ws_bytes = scldpc_bp_stream_workspace_bytes(d, cfg->flags);
-    if (vn_cn.alloc(4 * G * E) || vn_slot.alloc(4 * G * E) || cn_edge.alloc(4 * G * nk * d->dc) || scratch.alloc(4 * G * nk) ||
-        ws.alloc(ws_bytes) || res.alloc(4 * 5 * G * B))
+    cudaStream_t st = host_call_stream();
+    if (vn_cn.alloc(4 * G * E, st) || vn_slot.alloc(4 * G * E, st) || cn_edge.alloc(4 * G * nk * d->dc, st) || scratch.alloc(4 * G * nk, st) ||
+        ws.alloc(ws_bytes, st) || res.alloc(4 * 5 * G * B, st))
         return fail(SCLDPC_ECUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaStream_t st = nullptr;
     CU(cudaMemcpyAsync(vn_cn.p, vn_cn_host, 4 * G * E, cudaMemcpyHostToDevice, st));
     scldpc_batch_t b{static_cast<int32_t *>(vn_cn.p), static_cast<int32_t *>(vn_slot.p), static_cast<int32_t *>(cn_edge.p), nullptr};
     if ((rc = scldpc_graph_build_tables(d, &b, static_cast<int32_t *>(scratch.p), st))) return rc;

@@ -473,7 +473,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
 
 
 namespace scldpc {
-// host-side instrumentation shared by the launchers (capi.cu owns the storage)
+// host-side instrumentation shared by the launchers (capi.cu owns the storage).  One instance per host thread: concurrent callers
+// neither share the launch counter nor each other's samples
 struct Profiler {
     long long launches;          // kernels launched by this library since the last reset
     int sample_every;            // 0 = off; otherwise time the sweeps of every sample_every-th iteration
@@ -481,5 +482,5 @@ struct Profiler {
     cudaEvent_t *ev;             // 3 events per sample: before CN sweep, between, after VN sweep
     int *iter_idx;
 };
-extern Profiler g_prof;
+extern thread_local Profiler g_prof;
 }  // namespace scldpc

@@ -270,7 +270,8 @@ void scldpc_philox_picks(uint64_t seed, uint64_t frame_id, int n, uint32_t *out_
 int scldpc_allreduce_counters(void *nccl_comm, int64_t *counters_dev, int n_int64, void *stream);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
-/* kernels launched by the library since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
+/* The launch counter and the sampling state are per calling host thread (concurrent callers do not interfere).
+ * kernels launched by the library (from this thread) since the last reset; scldpc_bp_sweep_stats: CN / VN positions swept by the last
  * scldpc_bp_full call on this workspace (wave tracking skips positions whose inputs did not change).  On the workspace
  * of a node-state scldpc_bp_stream call (flags SCLDPC_F_STREAM): out[0] = lane compactions done in the tails of the
  * graphs' streams, out[1] = frames they moved */
