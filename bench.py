@@ -815,24 +815,43 @@ def run_ours(args):
                                               *[ctypes.c_void_p(o.data_ptr()) for o in outs], None, None, None, 0))
             return int(outs[0].sum().item())
 
-    for j in range(nw_e2e):
-        e2e_step(j)
-    barrier()
-    t0 = time.perf_counter()
+    # warm-up and timed calls of a batch slot run on the same host thread: the library gives every calling thread its own stream
+    # (and the memory pool hands a thread's freed buffers back to it without a detour)
     e_parts = [0] * P
+    gate0, gate1 = threading.Barrier(P + 1), threading.Barrier(P + 1)
+
+    e_err = []
 
     def e2e_worker(t):
-        for j in range(t, args.steps, P):
-            e_parts[t] += e2e_step(nw_e2e + j, t)    # the call returns after its D2H copy has completed
+        try:
+            torch.cuda.set_device(local_rank)
+            for j in range(t, max(nw_e2e, P if nw_e2e else 0), P):
+                e2e_step(j % max(1, nw_e2e), t)      # untimed
+            gate0.wait()
+            gate1.wait()
+            for j in range(t, args.steps, P):
+                e_parts[t] += e2e_step(nw_e2e + j, t)    # the call returns after its D2H copy has completed
+        except threading.BrokenBarrierError:         # another slot failed
+            pass
+        except Exception as e:  # pragma: no cover
+            e_err.append(e)
+            gate0.abort()
+            gate1.abort()
 
-    if P == 1:
-        e2e_worker(0)
-    else:                                            # P host threads, each call on its own thread's stream inside the library
-        th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(P)]
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
+    th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(P)]
+    for x in th:
+        x.start()
+    try:
+        gate0.wait()                                 # every slot has warmed up
+        barrier()
+        t0 = time.perf_counter()
+        gate1.wait()
+    except threading.BrokenBarrierError:
+        t0 = time.perf_counter()
+    for x in th:
+        x.join()
+    if e_err:
+        raise e_err[0]
     e_iters = sum(e_parts)
     torch.cuda.synchronize()
     e_dt = time.perf_counter() - t0
