@@ -17,6 +17,8 @@
  *    void* (NULL = default stream).  Every function returns 0 on success and a negative SCLDPC_E* code on
  *    failure; scldpc_last_error() returns a thread-local message.  There is NO CPU fallback: without a CUDA
  *    device every compute entry point fails with SCLDPC_ECUDA.
+ *  - Host threads may call concurrently on different streams / workspaces: all library state is per calling thread.
+ *    The *_host entry points (host buffers in, host buffers out) work on a stream owned by the calling thread.
  *  - A batch holds n_graphs independent graph realisations; each graph decodes 64*n_words frames at once,
  *    bit-sliced: bit b of 64-bit word w of a node is that node's value in frame 64*w+b of the graph.
  *    n_words must be a power of two in [2,16].
