@@ -272,7 +272,7 @@ __global__ void ns_settle_done_kernel(BpParams p)
 // The harvest hands out consecutive frame ids in ascending lane order, so the armed lanes of a graph are one run of frame ids
 // [f0, f0+A) and one Philox call -- four frames of one VN -- serves four armed lanes wherever they sit in the row.  A block takes
 // tiles of ARM_ROWS VN rows: phase 1 spreads (row, Philox block) pairs over the threads and ORs the erased frames into a shared
-// copy of the rows' armed bits (exactly ceil(A/4) calls per VN, against one call per armed lane and 128-lane chunk when every
+// copy of the rows' armed bits (at most ceil(A/4)+1 calls per VN, against one call per armed lane and 128-lane chunk when every
 // thread drew the lanes of its own chunk: the kernel was 7.8 % of the benchmarked step, profiles/r02e); phase 2 merges the tile
 // into both planes with coalesced 16-byte accesses.
 #define ARM_ROWS 128
