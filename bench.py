@@ -411,6 +411,61 @@ def side_workloads(args, dev, side_cpu):
                                      "frame_error_rate": nfail / frames, "gpu_launches": launches}
             del fb, acc
             torch.cuda.empty_cache()
+        # the one-frame-per-lane layout with two batches in flight (as in the headline): all of a 1024-frame stream is tail, so
+        # the next batch's graphs fill the machine while the stalled frames of this one finish
+        import threading
+        Pp, G, nw, steps = 2, 4, 16, 8
+        fbs = [eng.FrameBatch(ens, G, 64 * nw, nw, device=dev) for _ in range(Pp)]
+        sts = [torch.cuda.Stream(device=dev) for _ in range(Pp)]
+        accs, nl, errs = [[] for _ in range(Pp)], [0] * Pp, []
+
+        def pstep(i, t):
+            gid = (2 << 20) + (i + 8) * G
+            fbs[t].generate_graphs(seed=args.seed, first_graph_id=gid)
+            res, _ = eng.decode_bp_stream(fbs[t], 1024, eps4, args.seed + 1, first_graph_id=gid, collect=False)
+            return res
+
+        def pworker(t, first, count, keep):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(sts[t]):
+                    lib.scldpc_launch_count(1)
+                    for i in range(first + t, first + count, Pp):
+                        r = pstep(i, t)
+                        if keep:
+                            accs[t].append(r)
+                    sts[t].synchronize()
+                    nl[t] = int(lib.scldpc_launch_count(1))
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        def prun(first, count, keep):
+            th = [threading.Thread(target=pworker, args=(t, first, count, keep)) for t in range(Pp)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            if errs:
+                raise errs[0]
+
+        prun(-Pp, Pp, False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prun(0, steps, True)
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) * 1e-3
+        rs = [r for a_ in accs for r in a_]
+        its = sum(int(r[0].sum().item()) for r in rs)
+        nfail = sum(int((r[1] > 0).sum().item()) for r in rs)
+        frames = steps * G * 1024
+        cfgs["n_words=16, two batches in flight"] = {"value": its * 2.0 * E_EDGES / dt, "unit": "edge-updates/s", "frames_per_s": frames / dt,
+                                                    "graphs_per_step": G, "lanes_per_graph": 64 * nw, "frames_per_graph": 1024, "steps": steps,
+                                                    "ms_per_step": 1e3 * dt / steps, "frame_error_rate": nfail / frames, "gpu_launches": sum(nl)}
+        del fbs, accs, rs
+        torch.cuda.empty_cache()
         best = max(cfgs, key=lambda k: cfgs[k]["value"])
         out["bp_full_fpg1024"] = dict(cfgs[best], layout=best, layouts=cfgs,
                                       note="scldpc_graph_generate + scldpc_graph_build_tables + fresh frame ids inside the timed region; every "
